@@ -1,0 +1,167 @@
+/*
+ * me_b200.h -- C ABI of the B200-native full-search block-matching estimator.
+ *
+ * This is the drop-in boundary for the reference's CPU search path.  The
+ * reference has no plugin/FFI layer: its search is the timed region of
+ * src/cpu/main.c:144-158 (thread pool -> runFindBestBlkMse -> findBestBlkMse ->
+ * findBestMatchMse -> computeMse, main.c:18-107).  Each entry point below names
+ * the reference interface it replaces.  Everything is extern "C", plain
+ * pointers and sizes, callable from C99; the implementation is hand-written
+ * sm_100a CUDA (motionestimation_b200/csrc/).  There is NO CPU fallback: every
+ * compute entry point returns ME_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Semantics (bit-exact with the reference CPU path):
+ *   blocks   nbx=ceil(W/B), nby=ceil(H/B), i=by*nbx+bx, partial edge blocks kept
+ *            (src/common/prediction_frame.c:9-23)
+ *   window   [x0-R, x0+w-1+R] x [y0-R, y0+h-1+R] clamped to the frame (main.c:69-76)
+ *   cost     SSD=sum (cur-ref)^2 accumulated in float, score=sum/(w*h)   (main.c:18-27)
+ *   winner   first strict minimum of score in y-major, x-minor order     (main.c:53-62)
+ *   output   mvx=x-x0, mvy=y-y0 (main.c:58-59,79), score (main.c:81), plus the exact
+ *            integer SSD of the winner (the reference keeps it only as the float sum)
+ */
+#ifndef ME_B200_H
+#define ME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "me_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_B200_ABI_VERSION 1
+
+/* return codes: 0 ok, negative error.  The library never prints or exits
+ * (the reference printf+exit()s, main.c:110-113,134-139; utils.c:105-108). */
+#define ME_OK               0
+#define ME_ERR_INVALID_ARG -1 /* NULL pointer, non-positive dimension, bad slot ...            */
+#define ME_ERR_UNSUPPORTED -2 /* cannot be represented: pixel outside 0..255, foreign block grid */
+#define ME_ERR_CUDA        -3 /* a CUDA call failed; see me_b200_last_error()                  */
+#define ME_ERR_NO_DEVICE   -4 /* no usable CUDA device (there is no CPU fallback)              */
+#define ME_ERR_NOMEM       -5
+#define ME_ERR_STATE       -6 /* wait on an idle slot, submit on a busy one                    */
+
+/* kernel selection (me_b200_create_ex).  AUTO picks the tuned kernel when the
+ * geometry allows it and the generic exact kernel otherwise; both give
+ * identical results. */
+#define ME_KERNEL_AUTO    0
+#define ME_KERNEL_GENERIC 1
+#define ME_KERNEL_TILED   2
+
+#define ME_B200_MAX_SLOTS 4
+
+typedef struct me_b200_ctx me_b200_ctx;
+
+int         me_b200_abi_version(void);
+const char *me_b200_strerror(int code);
+/* text of the last CUDA failure seen by this context (or by the implicit
+ * context of me_b200_search when ctx == NULL). */
+const char *me_b200_last_error(const me_b200_ctx *ctx);
+/* number of CUDA devices visible, 0 if none / no driver. */
+int         me_b200_device_count(void);
+
+/* ---- context: one per GPU and geometry --------------------------------------
+ * replaces: the per-run setup of main.c:117-143 (blkDim, extraSpan, W, H;
+ * createPredictionFrame).  Owns all device memory; caller owns all host memory. */
+int  me_b200_create(me_b200_ctx **ctx, int device, int width, int height,
+                    int blk_dim, int extra_span);
+/* max_pairs: largest batch one call may carry (>=1); kernel: ME_KERNEL_*. */
+int  me_b200_create_ex(me_b200_ctx **ctx, int device, int width, int height,
+                       int blk_dim, int extra_span, int max_pairs, int kernel);
+void me_b200_destroy(me_b200_ctx *ctx);
+
+int      me_b200_num_blocks(const me_b200_ctx *ctx);   /* prediction_frame.c:9-12 */
+int      me_b200_blocks_x(const me_b200_ctx *ctx);
+int      me_b200_blocks_y(const me_b200_ctx *ctx);
+int      me_b200_kernel_in_use(const me_b200_ctx *ctx); /* ME_KERNEL_GENERIC or _TILED */
+/* exact work counts of one frame pair */
+uint64_t me_b200_pixel_compares(const me_b200_ctx *ctx);
+uint64_t me_b200_candidates(const me_b200_ctx *ctx);
+/* kernel launches issued by this context so far (search + pack kernels) */
+uint64_t me_b200_launch_count(const me_b200_ctx *ctx);
+
+/* ---- reference drop-in ---------------------------------------------------------
+ * replaces: the whole dispatch loop main.c:144-158, i.e. one call instead of
+ * num_blks x thpool_add_work(runFindBestBlkMse).  pf->frame is the current
+ * frame, refFrame the reference frame, both `int` per pixel (utils.c:49-53).
+ * On success every pf->blks[i] has motion_vectorX/Y filled and
+ * is_best_match_found = 1 (populateBlkMotionVector, main.c:11-15), which
+ * motionCompensatedFrame requires (utils.c:105-108).
+ * Optional out arrays (may be NULL), num_blks entries each: scores[i] = the
+ * float findBestBlkMse returns (main.c:81), ssd[i] = exact integer SSD.
+ * Uses an internal context cached per (device, W, H, B, R); device from env
+ * ME_B200_DEVICE (default 0).  Blocking; not re-entrant for the same geometry. */
+int me_b200_search(predictionFrame *pf, const int *refFrame, int extraSpan);
+int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpan,
+                          float *scores, uint32_t *ssd);
+/* frees the cached implicit contexts (optional; also done at process exit). */
+void me_b200_release_cached(void);
+
+/* ---- host u8 path ----------------------------------------------------------------
+ * replaces: yuvReadFrame's uint8 -> int widening (utils.c:61-73) + the search.
+ * cur/ref: npairs frame pairs, 8-bit luma, row-major, stride == width, pair p at
+ * cur + p*W*H.  Outputs: npairs*num_blocks entries each, any may be NULL.
+ * Blocking: H2D, search, D2H. */
+int me_b200_search_u8(me_b200_ctx *ctx, const uint8_t *cur, const uint8_t *ref, int npairs,
+                      int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
+
+/* pipelined form: up to ME_B200_MAX_SLOTS batches in flight, each slot on its
+ * own stream (H2D of slot k+1 overlaps the search of slot k).  Host buffers
+ * should be pinned (me_b200_host_alloc) for the copies to be asynchronous and
+ * must stay valid until me_b200_wait(slot) returns. */
+int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t *ref, int npairs,
+                   int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
+int me_b200_wait(me_b200_ctx *ctx, int slot);
+void *me_b200_host_alloc(size_t bytes); /* pinned; NULL on failure */
+void  me_b200_host_free(void *p);
+
+/* ---- device-resident path -----------------------------------------------------
+ * All pointers are DEVICE pointers on ctx's device.  Frames: u8, row pitch
+ * `pitch` bytes (>= width), pair p at d_cur + p*pair_stride.  Outputs
+ * npairs*num_blocks entries, any may be NULL.  Enqueued on `stream` (a
+ * cudaStream_t passed as void*, NULL = default stream); returns without
+ * synchronising.  The tuned kernel needs 16-byte aligned base/pitch/pair_stride
+ * (TMA); other layouts run the generic kernel. */
+int me_b200_search_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                          size_t pitch, size_t pair_stride, int npairs,
+                          int32_t *d_mvx, int32_t *d_mvy, uint32_t *d_ssd, float *d_score,
+                          void *stream);
+/* same, restricted to block rows [by_begin, by_end) of every pair -- the band
+ * sharding of one very large frame over several GPUs.
+ * Output arrays are still indexed by the global block index. */
+int me_b200_search_device_band(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                               size_t pitch, size_t pair_stride, int npairs,
+                               int by_begin, int by_end,
+                               int32_t *d_mvx, int32_t *d_mvy, uint32_t *d_ssd, float *d_score,
+                               void *stream);
+
+/* ---- post-search stage on device ------------------------
+ * replaces: main.c:160-168 (motionCompensatedFrame + 2x frameDiff, utils.c:94-134).
+ * d_out5: 5 stacked W x H u8 planes (ref, cur, mc, |ref-cur|, |mc-cur|), stride W.
+ * d_sq_err (may be NULL): one uint64 = sum (mc-cur)^2, d_max (may be NULL): one
+ * uint32 = max pixel of mc and cur -- the two inputs of imagePSNR (utils.c:137-164). */
+int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                               size_t pitch, const int32_t *d_mvx, const int32_t *d_mvy,
+                               uint8_t *d_out5, unsigned long long *d_sq_err, uint32_t *d_max,
+                               void *stream);
+
+/* ---- integer-pipe microbenchmark (defines the roofline denominator) ---------------
+ * Runs `which` (ME_PEAK_*) on `device` for about `iters` loop trips per thread
+ * and returns lane-instructions per second of the named SASS op (0 on error). */
+#define ME_PEAK_IDP4A        0 /* IDP.4A.U8.U8                          */
+#define ME_PEAK_VABSDIFF4    1 /* VABSDIFF4.U8                          */
+#define ME_PEAK_SSD_PAIR     2 /* VABSDIFF4 + IDP.4A pairs (4 px / pair) */
+#define ME_PEAK_IADD3        3
+#define ME_PEAK_LOP3         4
+#define ME_PEAK_IMAD         5
+#define ME_PEAK_VIMNMX       6
+#define ME_PEAK_SSD_PAIR_LDS 7 /* pairs + 1 LDS.32 per 16 pairs          */
+#define ME_PEAK_IDP4A_IADD3  8 /* IDP.4A + IADD3 1:1 (do the two pipes overlap?) */
+#define ME_PEAK_COUNT        9
+double me_b200_int_peak(int device, int which, int iters, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

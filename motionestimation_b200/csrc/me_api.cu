@@ -1,0 +1,502 @@
+// me_api.cu -- implementation of the C ABI declared in include/me_b200.h.
+// Host-side plumbing only: contexts, device buffers, streams, copies, launches.
+// All arithmetic of the search lives in me_generic.cu / me_tiled.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <new>
+
+#include "me_b200.h"
+#include "me_device.cuh"
+
+struct me_slot {
+  cudaStream_t stream = nullptr;
+  uint8_t *d_cur = nullptr, *d_ref = nullptr;  // max_pairs frames each, pitch = ctx->pitch
+  int32_t *d_mvx = nullptr, *d_mvy = nullptr;
+  uint32_t *d_ssd = nullptr;
+  float *d_score = nullptr;
+  bool busy = false;
+};
+
+struct me_b200_ctx {
+  int device = 0;
+  me::Geom g{};
+  int nb = 0;
+  int max_pairs = 1;
+  int kernel_req = ME_KERNEL_AUTO;
+  int kernel = ME_KERNEL_GENERIC;  // what the internal (slot) path runs
+  size_t pitch = 0, frame_bytes = 0;
+  me_slot slots[ME_B200_MAX_SLOTS];
+  me::TiledPlan *plan = nullptr;
+  uint64_t launches = 0;
+  char err[256] = {0};
+  // scratch for the int-frame drop-in path
+  uint8_t *h_cur = nullptr, *h_ref = nullptr;  // pinned, W*H each
+  int32_t *h_mvx = nullptr, *h_mvy = nullptr;
+  uint32_t *h_ssd = nullptr;
+  float *h_score = nullptr;
+};
+
+namespace {
+
+char g_err[256] = {0};
+
+int fail_cuda(me_b200_ctx *ctx, cudaError_t e, const char *what) {
+  char *dst = ctx ? ctx->err : g_err;
+  snprintf(dst, 256, "%s: %s", what, cudaGetErrorString(e));
+  (void)cudaGetLastError();
+  return ME_ERR_CUDA;
+}
+
+#define ME_CUDA(ctx, call)                                    \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+  } while (0)
+
+uint64_t axis_sum(int N, int B, int R, bool weighted) {
+  uint64_t s = 0;
+  for (int p = 0; p < N; p += B) {
+    int e = p + B < N ? B : N - p;
+    int lo = p - R < 0 ? 0 : p - R;
+    int hi = p + e - 1 + R >= N ? N - 1 : p + e - 1 + R;
+    uint64_t nc = (uint64_t)(hi - e + 1 - lo + 1);
+    s += weighted ? nc * (uint64_t)e : nc;
+  }
+  return s;
+}
+
+
+// Pick + launch the search for frames already on the device.
+int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, int by_end,
+               const me::Out &o, cudaStream_t s) {
+  me::Geom g = ctx->g;
+  g.by_begin = by_begin;
+  g.by_count = by_end - by_begin;
+  if (g.by_count <= 0 || npairs <= 0) return ME_OK;
+  bool tiled = ctx->kernel_req != ME_KERNEL_GENERIC && ctx->plan &&
+               me::tiled_supported(g, f.pitch, f.pair_stride, f.cur, f.ref);
+  if (ctx->kernel_req == ME_KERNEL_TILED && !tiled) {
+    snprintf(ctx->err, 256, "tiled kernel requested but geometry/layout unsupported");
+    return ME_ERR_UNSUPPORTED;
+  }
+  if (tiled) {
+    const char *txt = nullptr;
+    cudaError_t e = me::launch_tiled(ctx->plan, g, f, npairs, o, s, &txt);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, txt ? txt : "launch_tiled");
+  } else {
+    // grid.y carries the pair index
+    int done = 0;
+    while (done < npairs) {
+      int n = npairs - done > 65535 ? 65535 : npairs - done;
+      me::Frames ff = f;
+      ff.cur += (size_t)done * f.pair_stride;
+      ff.ref += (size_t)done * f.pair_stride;
+      me::Out oo = o;
+      size_t off = (size_t)done * ctx->nb;
+      if (oo.mvx) oo.mvx += off;
+      if (oo.mvy) oo.mvy += off;
+      if (oo.ssd) oo.ssd += off;
+      if (oo.score) oo.score += off;
+      cudaError_t e = me::launch_generic(g, ff, n, oo, s);
+      if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_generic");
+      ctx->launches++;
+      done += n;
+    }
+    return ME_OK;
+  }
+  ctx->launches++;
+  return ME_OK;
+}
+
+int use_device(me_b200_ctx *ctx) {
+  ME_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int me_b200_abi_version(void) { return ME_B200_ABI_VERSION; }
+
+const char *me_b200_strerror(int code) {
+  switch (code) {
+    case ME_OK: return "ok";
+    case ME_ERR_INVALID_ARG: return "invalid argument";
+    case ME_ERR_UNSUPPORTED: return "unsupported input (not representable)";
+    case ME_ERR_CUDA: return "CUDA error";
+    case ME_ERR_NO_DEVICE: return "no usable CUDA device (no CPU fallback exists)";
+    case ME_ERR_NOMEM: return "out of memory";
+    case ME_ERR_STATE: return "slot state error";
+    default: return "unknown error";
+  }
+}
+
+const char *me_b200_last_error(const me_b200_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+int me_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int me_b200_create(me_b200_ctx **ctx, int device, int width, int height, int blk_dim, int extra_span) {
+  return me_b200_create_ex(ctx, device, width, height, blk_dim, extra_span, 1, ME_KERNEL_AUTO);
+}
+
+int me_b200_create_ex(me_b200_ctx **out, int device, int width, int height, int blk_dim,
+                      int extra_span, int max_pairs, int kernel) {
+  if (!out) return ME_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (width <= 0 || height <= 0 || blk_dim <= 0 || extra_span < 0 || max_pairs < 1) return ME_ERR_INVALID_ARG;
+  if (kernel != ME_KERNEL_AUTO && kernel != ME_KERNEL_GENERIC && kernel != ME_KERNEL_TILED)
+    return ME_ERR_INVALID_ARG;
+  if (blk_dim > 256 || extra_span > 1024) return ME_ERR_UNSUPPORTED;
+  if ((long long)width * height > (1ll << 30)) return ME_ERR_UNSUPPORTED;
+  int n = me_b200_device_count();
+  if (n <= 0 || device < 0 || device >= n) return ME_ERR_NO_DEVICE;
+
+  me_b200_ctx *ctx = new (std::nothrow) me_b200_ctx();
+  if (!ctx) return ME_ERR_NOMEM;
+  ctx->device = device;
+  ctx->g.W = width;
+  ctx->g.H = height;
+  ctx->g.B = blk_dim;
+  ctx->g.R = extra_span;
+  ctx->g.nbx = (width + blk_dim - 1) / blk_dim;
+  ctx->g.nby = (height + blk_dim - 1) / blk_dim;
+  ctx->g.by_begin = 0;
+  ctx->g.by_count = ctx->g.nby;
+  ctx->nb = ctx->g.nbx * ctx->g.nby;
+  ctx->max_pairs = max_pairs;
+  ctx->kernel_req = kernel;
+  ctx->pitch = ((size_t)width + 15) & ~(size_t)15;  // TMA: global row stride multiple of 16 B
+  ctx->frame_bytes = ctx->pitch * (size_t)height;
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    fail_cuda(nullptr, e, "cudaSetDevice");
+    delete ctx;
+    return ME_ERR_NO_DEVICE;
+  }
+  int rc = ME_OK;
+  auto check = [&](cudaError_t ce, const char *what) {
+    if (ce != cudaSuccess && rc == ME_OK) {
+      fail_cuda(nullptr, ce, what);
+      rc = ce == cudaErrorMemoryAllocation ? ME_ERR_NOMEM : ME_ERR_CUDA;
+    }
+  };
+  const size_t fb = ctx->frame_bytes * (size_t)max_pairs + 256;  // tail slack for TMA boxes
+  const size_t ob = (size_t)ctx->nb * (size_t)max_pairs;
+  for (int i = 0; i < ME_B200_MAX_SLOTS && rc == ME_OK; i++) {
+    me_slot &s = ctx->slots[i];
+    check(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    check(cudaMalloc(&s.d_cur, fb), "cudaMalloc(cur)");
+    check(cudaMalloc(&s.d_ref, fb), "cudaMalloc(ref)");
+    check(cudaMalloc(&s.d_mvx, ob * 4), "cudaMalloc(mvx)");
+    check(cudaMalloc(&s.d_mvy, ob * 4), "cudaMalloc(mvy)");
+    check(cudaMalloc(&s.d_ssd, ob * 4), "cudaMalloc(ssd)");
+    check(cudaMalloc(&s.d_score, ob * 4), "cudaMalloc(score)");
+    if (rc == ME_OK) {
+      check(cudaMemsetAsync(s.d_cur, 0, fb, s.stream), "memset");
+      check(cudaMemsetAsync(s.d_ref, 0, fb, s.stream), "memset");
+    }
+  }
+  if (rc == ME_OK && kernel != ME_KERNEL_GENERIC) {
+    cudaError_t pe = me::tiled_plan_create(&ctx->plan, ctx->g, max_pairs);
+    if (pe != cudaSuccess) {
+      ctx->plan = nullptr;
+      (void)cudaGetLastError();
+      if (kernel == ME_KERNEL_TILED) {
+        fail_cuda(nullptr, pe, "tiled_plan_create");
+        rc = ME_ERR_UNSUPPORTED;
+      }
+    }
+  }
+  if (rc == ME_OK) {
+    me::Frames f{ctx->slots[0].d_cur, ctx->slots[0].d_ref, ctx->pitch, ctx->frame_bytes};
+    ctx->kernel = (ctx->plan && me::tiled_supported(ctx->g, f.pitch, f.pair_stride, f.cur, f.ref))
+                      ? ME_KERNEL_TILED
+                      : ME_KERNEL_GENERIC;
+    if (kernel == ME_KERNEL_TILED && ctx->kernel != ME_KERNEL_TILED) {
+      snprintf(g_err, 256, "tiled kernel does not support B=%d R=%d", blk_dim, extra_span);
+      rc = ME_ERR_UNSUPPORTED;
+    }
+  }
+  if (rc == ME_OK) check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  if (rc != ME_OK) {
+    me_b200_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return ME_OK;
+}
+
+void me_b200_destroy(me_b200_ctx *ctx) {
+  if (!ctx) return;
+  if (cudaSetDevice(ctx->device) == cudaSuccess) {
+    for (int i = 0; i < ME_B200_MAX_SLOTS; i++) {
+      me_slot &s = ctx->slots[i];
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      cudaFree(s.d_cur);
+      cudaFree(s.d_ref);
+      cudaFree(s.d_mvx);
+      cudaFree(s.d_mvy);
+      cudaFree(s.d_ssd);
+      cudaFree(s.d_score);
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (ctx->plan) me::tiled_plan_destroy(ctx->plan);
+    cudaFreeHost(ctx->h_cur);
+    cudaFreeHost(ctx->h_ref);
+    cudaFreeHost(ctx->h_mvx);
+    cudaFreeHost(ctx->h_mvy);
+    cudaFreeHost(ctx->h_ssd);
+    cudaFreeHost(ctx->h_score);
+    (void)cudaGetLastError();
+  }
+  delete ctx;
+}
+
+int me_b200_num_blocks(const me_b200_ctx *ctx) { return ctx ? ctx->nb : 0; }
+int me_b200_blocks_x(const me_b200_ctx *ctx) { return ctx ? ctx->g.nbx : 0; }
+int me_b200_blocks_y(const me_b200_ctx *ctx) { return ctx ? ctx->g.nby : 0; }
+int me_b200_kernel_in_use(const me_b200_ctx *ctx) { return ctx ? ctx->kernel : 0; }
+uint64_t me_b200_pixel_compares(const me_b200_ctx *ctx) {
+  if (!ctx) return 0;
+  return axis_sum(ctx->g.W, ctx->g.B, ctx->g.R, true) * axis_sum(ctx->g.H, ctx->g.B, ctx->g.R, true);
+}
+uint64_t me_b200_candidates(const me_b200_ctx *ctx) {
+  if (!ctx) return 0;
+  return axis_sum(ctx->g.W, ctx->g.B, ctx->g.R, false) * axis_sum(ctx->g.H, ctx->g.B, ctx->g.R, false);
+}
+uint64_t me_b200_launch_count(const me_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *me_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void me_b200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t *ref, int npairs,
+                   int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score) {
+  if (!ctx || !cur || !ref || slot < 0 || slot >= ME_B200_MAX_SLOTS) return ME_ERR_INVALID_ARG;
+  if (npairs < 1 || npairs > ctx->max_pairs) return ME_ERR_INVALID_ARG;
+  me_slot &s = ctx->slots[slot];
+  if (s.busy) return ME_ERR_STATE;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  const size_t W = (size_t)ctx->g.W, H = (size_t)ctx->g.H;
+  // pairs are contiguous on the host (stride W) and on the device (pitch): one 2-D copy each
+  ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs,
+                                 cudaMemcpyHostToDevice, s.stream));
+  ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs,
+                                 cudaMemcpyHostToDevice, s.stream));
+  me::Frames f{s.d_cur, s.d_ref, ctx->pitch, ctx->frame_bytes};
+  me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
+  rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
+  if (rc) return rc;
+  const size_t ob = (size_t)ctx->nb * (size_t)npairs * 4;
+  if (mvx) ME_CUDA(ctx, cudaMemcpyAsync(mvx, s.d_mvx, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (mvy) ME_CUDA(ctx, cudaMemcpyAsync(mvy, s.d_mvy, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (ssd) ME_CUDA(ctx, cudaMemcpyAsync(ssd, s.d_ssd, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (score) ME_CUDA(ctx, cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream));
+  s.busy = true;
+  return ME_OK;
+}
+
+int me_b200_wait(me_b200_ctx *ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= ME_B200_MAX_SLOTS) return ME_ERR_INVALID_ARG;
+  me_slot &s = ctx->slots[slot];
+  if (!s.busy) return ME_ERR_STATE;
+  s.busy = false;
+  ME_CUDA(ctx, cudaStreamSynchronize(s.stream));
+  return ME_OK;
+}
+
+int me_b200_search_u8(me_b200_ctx *ctx, const uint8_t *cur, const uint8_t *ref, int npairs,
+                      int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score) {
+  if (!ctx || !cur || !ref || npairs < 1) return ME_ERR_INVALID_ARG;
+  // batches larger than the context was sized for go through in max_pairs chunks
+  const size_t fsz = (size_t)ctx->g.W * ctx->g.H;
+  int done = 0, inflight[ME_B200_MAX_SLOTS], k = 0;
+  for (int i = 0; i < ME_B200_MAX_SLOTS; i++) inflight[i] = 0;
+  int rc = ME_OK;
+  while (done < npairs && rc == ME_OK) {
+    int slot = k % ME_B200_MAX_SLOTS;
+    if (inflight[slot]) {
+      rc = me_b200_wait(ctx, slot);
+      inflight[slot] = 0;
+      if (rc) break;
+    }
+    int n = npairs - done > ctx->max_pairs ? ctx->max_pairs : npairs - done;
+    size_t oo = (size_t)done * ctx->nb;
+    rc = me_b200_submit(ctx, slot, cur + done * fsz, ref + done * fsz, n, mvx ? mvx + oo : nullptr,
+                        mvy ? mvy + oo : nullptr, ssd ? ssd + oo : nullptr, score ? score + oo : nullptr);
+    if (rc == ME_OK) inflight[slot] = 1;
+    done += n;
+    k++;
+  }
+  for (int i = 0; i < ME_B200_MAX_SLOTS; i++)
+    if (inflight[i]) {
+      int r2 = me_b200_wait(ctx, i);
+      if (rc == ME_OK) rc = r2;
+    }
+  return rc;
+}
+
+int me_b200_search_device_band(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                               size_t pitch, size_t pair_stride, int npairs, int by_begin, int by_end,
+                               int32_t *d_mvx, int32_t *d_mvy, uint32_t *d_ssd, float *d_score,
+                               void *stream) {
+  if (!ctx || !d_cur || !d_ref || npairs < 1) return ME_ERR_INVALID_ARG;
+  if (pitch < (size_t)ctx->g.W) return ME_ERR_INVALID_ARG;
+  if (npairs > 1 && pair_stride < pitch * (size_t)ctx->g.H) return ME_ERR_INVALID_ARG;
+  if (by_begin < 0 || by_end > ctx->g.nby || by_begin > by_end) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  me::Frames f{d_cur, d_ref, pitch, pair_stride};
+  me::Out o{d_mvx, d_mvy, d_ssd, d_score};
+  return run_search(ctx, f, npairs, by_begin, by_end, o, (cudaStream_t)stream);
+}
+
+int me_b200_search_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref, size_t pitch,
+                          size_t pair_stride, int npairs, int32_t *d_mvx, int32_t *d_mvy,
+                          uint32_t *d_ssd, float *d_score, void *stream) {
+  if (!ctx) return ME_ERR_INVALID_ARG;
+  return me_b200_search_device_band(ctx, d_cur, d_ref, pitch, pair_stride, npairs, 0, ctx->g.nby, d_mvx,
+                                    d_mvy, d_ssd, d_score, stream);
+}
+
+int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                               size_t pitch, const int32_t *d_mvx, const int32_t *d_mvy,
+                               uint8_t *d_out5, unsigned long long *d_sq_err, uint32_t *d_max,
+                               void *stream) {
+  if (!ctx || !d_cur || !d_ref || !d_mvx || !d_mvy || !d_out5) return ME_ERR_INVALID_ARG;
+  if (pitch < (size_t)ctx->g.W) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  cudaError_t e = me::launch_postprocess(ctx->g, d_cur, d_ref, pitch, d_mvx, d_mvy, d_out5, d_sq_err,
+                                         d_max, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_postprocess");
+  ctx->launches++;
+  return ME_OK;
+}
+
+// ---- reference drop-in: int frames + predictionFrame -------------------------------
+
+namespace {
+struct cached_ctx {
+  int device, W, H, B, R;
+  me_b200_ctx *ctx;
+};
+std::mutex g_cache_mu;
+cached_ctx g_cache[8];
+int g_cache_n = 0;
+bool g_atexit = false;
+
+int env_device() {
+  const char *e = getenv("ME_B200_DEVICE");
+  return e ? atoi(e) : 0;
+}
+
+// int -> u8 with a range check (values the reference would treat as plain ints
+// outside 0..255 cannot be represented in the 8-bit device layout)
+bool pack_u8(uint8_t *dst, const int *src, size_t n) {
+  unsigned bad = 0;
+  for (size_t i = 0; i < n; i++) {
+    unsigned v = (unsigned)src[i];
+    bad |= v;
+    dst[i] = (uint8_t)v;
+  }
+  return (bad & ~0xffu) == 0;
+}
+}  // namespace
+
+void me_b200_release_cached(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (int i = 0; i < g_cache_n; i++) me_b200_destroy(g_cache[i].ctx);
+  g_cache_n = 0;
+}
+
+int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpan, float *scores,
+                          uint32_t *ssd) {
+  if (!pf || !pf->frame || !pf->blks || !refFrame) return ME_ERR_INVALID_ARG;
+  if (pf->width <= 0 || pf->height <= 0 || pf->blk_dim <= 0 || extraSpan < 0) return ME_ERR_INVALID_ARG;
+  const int W = pf->width, H = pf->height, B = pf->blk_dim;
+  const int nbx = (W + B - 1) / B, nby = (H + B - 1) / B;
+  if (pf->num_blks != nbx * nby) return ME_ERR_UNSUPPORTED;
+  // the grid must be the raster tiling createPredictionFrame builds (prediction_frame.c:14-23)
+  for (int i = 0; i < pf->num_blks; i++) {
+    const block &b = pf->blks[i];
+    const int x0 = (i % nbx) * B, y0 = (i / nbx) * B;
+    const int w = x0 + B < W ? B : W - x0, h = y0 + B < H ? B : H - y0;
+    if (b.top_left_x != x0 || b.top_left_y != y0 || b.width != w || b.height != h)
+      return ME_ERR_UNSUPPORTED;
+  }
+  const int device = env_device();
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  me_b200_ctx *ctx = nullptr;
+  for (int i = 0; i < g_cache_n; i++)
+    if (g_cache[i].device == device && g_cache[i].W == W && g_cache[i].H == H && g_cache[i].B == B &&
+        g_cache[i].R == extraSpan)
+      ctx = g_cache[i].ctx;
+  if (!ctx) {
+    int rc = me_b200_create_ex(&ctx, device, W, H, B, extraSpan, 1, ME_KERNEL_AUTO);
+    if (rc) return rc;
+    if (g_cache_n == 8) {
+      me_b200_destroy(g_cache[0].ctx);
+      memmove(&g_cache[0], &g_cache[1], sizeof(cached_ctx) * 7);
+      g_cache_n = 7;
+    }
+    g_cache[g_cache_n++] = cached_ctx{device, W, H, B, extraSpan, ctx};
+    if (!g_atexit) {
+      g_atexit = true;
+      atexit(me_b200_release_cached);
+    }
+  }
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  const size_t n = (size_t)W * H, nb = (size_t)ctx->nb;
+  if (!ctx->h_cur) {
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_cur, n, cudaHostAllocDefault));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_ref, n, cudaHostAllocDefault));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mvx, nb * 4, cudaHostAllocDefault));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_mvy, nb * 4, cudaHostAllocDefault));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_ssd, nb * 4, cudaHostAllocDefault));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_score, nb * 4, cudaHostAllocDefault));
+  }
+  if (!pack_u8(ctx->h_cur, pf->frame, n) || !pack_u8(ctx->h_ref, refFrame, n)) return ME_ERR_UNSUPPORTED;
+  rc = me_b200_submit(ctx, 0, ctx->h_cur, ctx->h_ref, 1, ctx->h_mvx, ctx->h_mvy, ctx->h_ssd, ctx->h_score);
+  if (rc) return rc;
+  rc = me_b200_wait(ctx, 0);
+  if (rc) return rc;
+  for (int i = 0; i < pf->num_blks; i++) {
+    block &b = pf->blks[i];
+    b.motion_vectorX = ctx->h_mvx[i];  // populateBlkMotionVector, main.c:11-15
+    b.motion_vectorY = ctx->h_mvy[i];
+    b.is_best_match_found = 1;
+  }
+  if (scores) memcpy(scores, ctx->h_score, nb * 4);
+  if (ssd) memcpy(ssd, ctx->h_ssd, nb * 4);
+  return ME_OK;
+}
+
+int me_b200_search(predictionFrame *pf, const int *refFrame, int extraSpan) {
+  return me_b200_search_scores(pf, refFrame, extraSpan, nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// me_device.cuh -- shared device-side declarations of the sm_100a search kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace me {
+
+// Frame geometry + search parameters, passed by value to every kernel.
+struct Geom {
+  int W, H;        // frame size in pixels
+  int B, R;        // block dimension, extra span (reference: blkDim, extraSpan)
+  int nbx, nby;    // ceil(W/B), ceil(H/B)                (prediction_frame.c:9-10)
+  int by_begin;    // first block row handled by this launch (band sharding)
+  int by_count;    // number of block rows handled
+};
+
+// SoA outputs, indexed pair * (nbx*nby) + block index; any pointer may be null.
+struct Out {
+  int32_t *mvx;
+  int32_t *mvy;
+  uint32_t *ssd;
+  float *score;
+};
+
+// Frames of a batch: u8, `pitch` bytes per row, pair p at base + p * pair_stride.
+struct Frames {
+  const uint8_t *cur;
+  const uint8_t *ref;
+  size_t pitch;
+  size_t pair_stride;
+};
+
+// host-side launchers (defined in the .cu files)
+cudaError_t launch_generic(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s);
+
+// Tiled kernel: returns false from tiled_supported() when the geometry is not
+// one it is specialised for (the caller then uses the generic kernel).
+bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref);
+struct TiledPlan;  // opaque: tensor maps + launch shape
+cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int max_pairs);
+void tiled_plan_destroy(TiledPlan *plan);
+cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
+                         cudaStream_t s, const char **err_text);
+
+cudaError_t launch_postprocess(const Geom &g, const uint8_t *cur, const uint8_t *ref, size_t pitch,
+                               const int32_t *mvx, const int32_t *mvy, uint8_t *out5,
+                               unsigned long long *sq_err, uint32_t *mx, cudaStream_t s);
+
+// order-preserving float -> u32 for non-negative floats
+__device__ __forceinline__ uint32_t score_bits(float s) { return __float_as_uint(s); }
+
+}  // namespace me

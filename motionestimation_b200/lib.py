@@ -1,0 +1,294 @@
+"""ctypes binding of the C ABI (``include/me_b200.h``) and the C host layer
+(``include/me_common.h``).  Names follow the reference's ``src/common`` interface:
+``Block`` = ``block`` (block.h:6-19), ``PredictionFrame`` = ``predictionFrame``
+(prediction_frame.h:8-16), ``create_prediction_frame`` = ``createPredictionFrame``
+(prediction_frame.c:3-25), ``search_prediction_frame`` = the dispatch loop of
+``src/cpu/main.c:144-158``.
+
+Device memory, streams and process groups come from torch (plumbing); the
+search itself always runs in ``libme_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+ME_OK = 0
+ME_ERR_INVALID_ARG = -1
+ME_ERR_UNSUPPORTED = -2
+ME_ERR_CUDA = -3
+ME_ERR_NO_DEVICE = -4
+ME_ERR_NOMEM = -5
+ME_ERR_STATE = -6
+ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED = 0, 1, 2
+ME_B200_MAX_SLOTS = 4
+
+PEAK_NAMES = ["IDP4A", "VABSDIFF4", "SSD_PAIR", "IADD3", "LOP3", "IMAD", "VIMNMX",
+              "SSD_PAIR_LDS", "IDP4A_IADD3"]
+
+
+class MeError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what}: error {code} ({_strerror(code)}) {detail}".strip())
+
+
+class Block(C.Structure):
+    """``block`` -- src/common/block.h:6-19 (11 ints, 44 bytes)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "idx_x", "idx_y", "top_left_x", "top_left_y", "bottom_right_x", "bottom_right_y",
+        "width", "height", "is_best_match_found", "motion_vectorX", "motion_vectorY")]
+
+
+class PredictionFrame(C.Structure):
+    """``predictionFrame`` -- src/common/prediction_frame.h:8-16."""
+    _fields_ = [("frame", C.POINTER(C.c_int)), ("width", C.c_int), ("height", C.c_int),
+                ("blk_dim", C.c_int), ("num_blks", C.c_int), ("blks", C.POINTER(Block))]
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libme_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Load ``libme_b200.so``; raises (loudly) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `make -C motionestimation_b200` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback.")
+    lib = C.CDLL(path)
+    vp, i32p, u32p, f32p, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    sig = {
+        "me_b200_abi_version": (C.c_int, []),
+        "me_b200_strerror": (C.c_char_p, [C.c_int]),
+        "me_b200_last_error": (C.c_char_p, [vp]),
+        "me_b200_device_count": (C.c_int, []),
+        "me_b200_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "me_b200_create_ex": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int]),
+        "me_b200_destroy": (None, [vp]),
+        "me_b200_num_blocks": (C.c_int, [vp]),
+        "me_b200_blocks_x": (C.c_int, [vp]),
+        "me_b200_blocks_y": (C.c_int, [vp]),
+        "me_b200_kernel_in_use": (C.c_int, [vp]),
+        "me_b200_pixel_compares": (C.c_uint64, [vp]),
+        "me_b200_candidates": (C.c_uint64, [vp]),
+        "me_b200_launch_count": (C.c_uint64, [vp]),
+        "me_b200_search": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int]),
+        "me_b200_search_scores": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int,
+                                            f32p, u32p]),
+        "me_b200_release_cached": (None, []),
+        "me_b200_search_u8": (C.c_int, [vp, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
+        "me_b200_submit": (C.c_int, [vp, C.c_int, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
+        "me_b200_wait": (C.c_int, [vp, C.c_int]),
+        "me_b200_host_alloc": (vp, [C.c_size_t]),
+        "me_b200_host_free": (None, [vp]),
+        "me_b200_search_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int,
+                                            i32p, i32p, u32p, f32p, vp]),
+        "me_b200_search_device_band": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int,
+                                                 C.c_int, C.c_int, i32p, i32p, u32p, f32p, vp]),
+        "me_b200_postprocess_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, i32p, i32p, u8p, vp, vp, vp]),
+        "me_b200_int_peak": (C.c_double, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+        # host layer (include/me_common.h)
+        "createBlk": (None, [C.POINTER(Block)] + [C.c_int] * 6),
+        "createPredictionFrame": (None, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int,
+                                         C.c_int, C.c_int]),
+        "getTimeStamp": (C.c_double, []),
+        "yuvReadFrame": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int]),
+        "yuvReadFrameU8": (C.c_int, [C.c_char_p, vp, C.c_int]),
+        "yuvWriteFrame": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int]),
+        "frameDiff": (None, [C.POINTER(C.c_int)] * 3 + [C.c_int]),
+        "motionCompensatedFrame": (C.c_int, [C.POINTER(C.c_int), PredictionFrame, C.POINTER(C.c_int)]),
+        "imagePSNR": (C.c_double, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by tests from include/*.h
+
+
+def _strerror(code: int) -> str:
+    try:
+        return load_library().me_b200_strerror(code).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def device_count() -> int:
+    return load_library().me_b200_device_count()
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Estimator:
+    """One search context (``me_b200_ctx``): one GPU, one geometry.
+
+    Replaces the per-run setup of ``src/cpu/main.c:117-143`` and, through
+    :meth:`search_u8` / :meth:`search_device`, the timed dispatch loop
+    ``main.c:144-158``.
+    """
+
+    def __init__(self, width: int, height: int, blk_dim: int = 8, extra_span: int = 12,
+                 device: int = 0, max_pairs: int = 1, kernel: int = ME_KERNEL_AUTO):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.me_b200_create_ex(C.byref(h), device, width, height, blk_dim, extra_span,
+                                         max_pairs, kernel)
+        if rc != ME_OK:
+            raise MeError(rc, "me_b200_create_ex", self._lib.me_b200_last_error(None).decode())
+        self._h = h
+        self.width, self.height, self.blk_dim, self.extra_span = width, height, blk_dim, extra_span
+        self.device, self.max_pairs = device, max_pairs
+        self.num_blocks = self._lib.me_b200_num_blocks(h)
+        self.blocks_x = self._lib.me_b200_blocks_x(h)
+        self.blocks_y = self._lib.me_b200_blocks_y(h)
+
+    # -- bookkeeping -----------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.me_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def kernel_in_use(self) -> int:
+        return self._lib.me_b200_kernel_in_use(self._h)
+
+    @property
+    def pixel_compares(self) -> int:
+        return int(self._lib.me_b200_pixel_compares(self._h))
+
+    @property
+    def candidates(self) -> int:
+        return int(self._lib.me_b200_candidates(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.me_b200_launch_count(self._h))
+
+    def _check(self, rc: int, what: str):
+        if rc != ME_OK:
+            raise MeError(rc, what, self._lib.me_b200_last_error(self._h).decode())
+
+    # -- host u8 path -------------------------------------------------------------------
+    def _host_args(self, cur, ref):
+        cur = np.ascontiguousarray(cur, dtype=np.uint8)
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        n = self.width * self.height
+        if cur.size != ref.size or cur.size % n:
+            raise ValueError("frames must be npairs x H x W uint8")
+        return cur, ref, cur.size // n
+
+    def search_u8(self, cur: np.ndarray, ref: np.ndarray):
+        """Blocking host-buffer search. Returns dict of (npairs, num_blocks) arrays."""
+        cur, ref, npairs = self._host_args(cur, ref)
+        out = self._alloc_out(npairs)
+        self._check(self._lib.me_b200_search_u8(self._h, _np_ptr(cur), _np_ptr(ref), npairs,
+                                                _np_ptr(out["mvx"]), _np_ptr(out["mvy"]),
+                                                _np_ptr(out["ssd"]), _np_ptr(out["score"])),
+                    "me_b200_search_u8")
+        return out
+
+    def _alloc_out(self, npairs: int):
+        nb = self.num_blocks
+        return {"mvx": np.empty((npairs, nb), np.int32), "mvy": np.empty((npairs, nb), np.int32),
+                "ssd": np.empty((npairs, nb), np.uint32), "score": np.empty((npairs, nb), np.float32)}
+
+    def submit_ptr(self, slot: int, cur_ptr: int, ref_ptr: int, npairs: int, mvx_ptr: int,
+                   mvy_ptr: int, ssd_ptr: int, score_ptr: int):
+        """Pipelined submit on raw (pinned) host pointers; pair with :meth:`wait`."""
+        self._check(self._lib.me_b200_submit(self._h, slot, cur_ptr, ref_ptr, npairs, mvx_ptr, mvy_ptr,
+                                             ssd_ptr or None, score_ptr or None), "me_b200_submit")
+
+    def wait(self, slot: int):
+        self._check(self._lib.me_b200_wait(self._h, slot), "me_b200_wait")
+
+    # -- device-resident path (torch tensors provide the memory) ---------------------------
+    def search_device(self, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int,
+                      d_mvx, d_mvy, d_ssd=None, d_score=None, stream: int = 0,
+                      by_begin: int = 0, by_end: Optional[int] = None):
+        """Enqueue the search on device pointers (ints or torch tensors)."""
+        def p(x):
+            if x is None:
+                return None
+            return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+        by_end = self.blocks_y if by_end is None else by_end
+        self._check(self._lib.me_b200_search_device_band(
+            self._h, p(d_cur), p(d_ref), pitch, pair_stride, npairs, by_begin, by_end,
+            p(d_mvx), p(d_mvy), p(d_ssd), p(d_score), stream or None), "me_b200_search_device_band")
+
+    def postprocess_device(self, d_cur, d_ref, pitch: int, d_mvx, d_mvy, d_out5, d_sq_err=None,
+                           d_max=None, stream: int = 0):
+        def p(x):
+            if x is None:
+                return None
+            return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+        self._check(self._lib.me_b200_postprocess_device(
+            self._h, p(d_cur), p(d_ref), pitch, p(d_mvx), p(d_mvy), p(d_out5), p(d_sq_err), p(d_max),
+            stream or None), "me_b200_postprocess_device")
+
+
+def create_prediction_frame(cur_int: np.ndarray, width: int, height: int, blk_dim: int) -> PredictionFrame:
+    """``createPredictionFrame`` (prediction_frame.c:3-25) on an int32 frame.
+    The returned struct borrows ``cur_int``'s memory; keep the array alive."""
+    lib = load_library()
+    assert cur_int.dtype == np.int32 and cur_int.size == width * height and cur_int.flags.c_contiguous
+    pf = PredictionFrame()
+    lib.createPredictionFrame(C.byref(pf), cur_int.ctypes.data_as(C.POINTER(C.c_int)), width, height, blk_dim)
+    pf._keepalive = cur_int
+    return pf
+
+
+def search_prediction_frame(pf: PredictionFrame, ref_int: np.ndarray, extra_span: int,
+                            want_scores: bool = False):
+    """The drop-in for ``main.c:144-158``: fills every block of ``pf``.
+    Returns (scores, ssd) arrays when ``want_scores``."""
+    lib = load_library()
+    assert ref_int.dtype == np.int32 and ref_int.flags.c_contiguous
+    refp = ref_int.ctypes.data_as(C.POINTER(C.c_int))
+    if want_scores:
+        sc = np.empty(pf.num_blks, np.float32)
+        sd = np.empty(pf.num_blks, np.uint32)
+        rc = lib.me_b200_search_scores(C.byref(pf), refp, extra_span, _np_ptr(sc), _np_ptr(sd))
+    else:
+        sc = sd = None
+        rc = lib.me_b200_search(C.byref(pf), refp, extra_span)
+    if rc != ME_OK:
+        raise MeError(rc, "me_b200_search", lib.me_b200_last_error(None).decode())
+    return sc, sd
+
+
+def int_peak(which: int, iters: int = 2000, device: int = 0):
+    """Integer-pipe microbenchmark: (lane-instructions/s, SM MHz during the run)."""
+    lib = load_library()
+    mhz = C.c_double(0.0)
+    rate = lib.me_b200_int_peak(device, which, iters, C.byref(mhz))
+    return rate, mhz.value
