@@ -1,0 +1,281 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of
+libme_b200.so and is compared bit for bit -- motion vectors, integer SSD and the
+float score bits -- with the oracle restatement and with the fixtures generated
+from the unmodified reference (tests/golden)."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import motionestimation_b200 as me
+from cases import CASES, make_frames, load_golden
+from oracle_binding import Oracle, ROOT
+
+pytestmark = pytest.mark.gpu
+
+META, FIELDS = load_golden()
+KERNELS = [me.ME_KERNEL_GENERIC, me.ME_KERNEL_AUTO]
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def check_against(out, p, exp_mvx, exp_mvy, exp_ssd, exp_bits, what=""):
+    bad = np.nonzero((out["mvx"][p] != exp_mvx) | (out["mvy"][p] != exp_mvy))[0]
+    assert bad.size == 0, f"{what}: {bad.size} MV mismatches, first block {bad[:5]}: got " \
+        f"({out['mvx'][p][bad[:5]]},{out['mvy'][p][bad[:5]]}) want ({exp_mvx[bad[:5]]},{exp_mvy[bad[:5]]})"
+    assert np.array_equal(out["ssd"][p], exp_ssd), f"{what}: ssd differs"
+    assert np.array_equal(out["score"][p].view(np.uint32), exp_bits), f"{what}: score bits differ"
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=["generic", "auto"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_golden_cases(case, kernel):
+    name, gen, args, B, R = case
+    cur, ref = make_frames(gen, args)
+    H, W = cur.shape
+    with me.Estimator(W, H, B, R, kernel=kernel) as est:
+        assert est.num_blocks == META[name]["blocks"]
+        out = est.search_u8(cur, ref)
+        assert est.launch_count >= 1
+    check_against(out, 0, FIELDS[name + "/mvx"].astype(np.int32), FIELDS[name + "/mvy"].astype(np.int32),
+                  FIELDS[name + "/ssd"], FIELDS[name + "/score_bits"], name)
+
+
+RANDOM_GEOMS = [
+    # B, R, W, H   (sizes not multiples of B, frames smaller than the window, R = 0)
+    (8, 12, 64, 48), (8, 12, 100, 60), (16, 32, 96, 80), (16, 32, 200, 104), (16, 64, 160, 144),
+    (8, 32, 128, 72), (4, 15, 33, 29), (5, 7, 41, 23), (7, 1, 30, 30), (32, 15, 80, 72),
+    (64, 7, 130, 70), (8, 0, 32, 32), (3, 2, 7, 5), (16, 32, 16, 16), (8, 12, 8, 8), (16, 8, 48, 40),
+    (16, 32, 208, 56), (8, 4, 72, 40), (16, 16, 64, 64), (8, 8, 352, 16),
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=["generic", "auto"])
+@pytest.mark.parametrize("B,R,W,H", RANDOM_GEOMS)
+def test_random_differential(orc, B, R, W, H, kernel):
+    pairs = [me.random_pair(W, H, B + R), me.shifted_noise_pair(W, H, seed=W + H, shift=(3, -2)),
+             me.constant_pair(W, H), me.checker_pair(W, H, 2), me.far_pair(W, H, 1)]
+    cur = np.stack([p[0] for p in pairs])
+    ref = np.stack([p[1] for p in pairs])
+    with me.Estimator(W, H, B, R, max_pairs=len(pairs), kernel=kernel) as est:
+        out = est.search_u8(cur, ref)
+    for p in range(len(pairs)):
+        o = orc.search(cur[p], ref[p], B, R)
+        check_against(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {p}")
+
+
+def test_drop_in_prediction_frame(orc):
+    """me_b200_search on the reference's own structs (replaces main.c:144-158)."""
+    cur8, ref8 = me.foreman(4), me.foreman(1)
+    cur, ref = cur8.astype(np.int32).ravel(), ref8.astype(np.int32).ravel()
+    pf = me.create_prediction_frame(cur, 352, 288, 8)
+    sc, sd = me.search_prediction_frame(pf, ref, 12, want_scores=True)
+    name = "foreman_yf4_yf1_8_12"
+    mvx = np.array([pf.blks[i].motion_vectorX for i in range(pf.num_blks)])
+    mvy = np.array([pf.blks[i].motion_vectorY for i in range(pf.num_blks)])
+    assert all(pf.blks[i].is_best_match_found == 1 for i in range(pf.num_blks))
+    assert np.array_equal(mvx, FIELDS[name + "/mvx"]) and np.array_equal(mvy, FIELDS[name + "/mvy"])
+    assert np.array_equal(sc.view(np.uint32), FIELDS[name + "/score_bits"])
+    assert np.array_equal(sd, FIELDS[name + "/ssd"])
+    # second call without scores, other geometry, then pixel range rejection
+    me.search_prediction_frame(pf, ref, 12)
+    bad = ref.copy()
+    bad[5] = 256
+    with pytest.raises(me.MeError) as ei:
+        me.search_prediction_frame(pf, bad, 12)
+    assert ei.value.code == me.ME_ERR_UNSUPPORTED
+    pf.blks[3].top_left_x += 1  # foreign grid
+    with pytest.raises(me.MeError) as ei:
+        me.search_prediction_frame(pf, ref, 12)
+    assert ei.value.code == me.ME_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("args,name", [((), "foreman_yf4_yf1_8_12"), (("4", "15"), "foreman_yf4_yf1_4_15"),
+                                       (("4", "7"), "foreman_yf4_yf1_4_7")])
+def test_cli_is_byte_identical(tmp_path, args, name):
+    """mes_b200: same argv, same PSNR line, same output_<B>_<R>.yuv bytes as the
+    reference binary (golden md5s from results/cpu/foreman)."""
+    exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200")
+    g = os.path.join(ROOT, "tests", "golden")
+    p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path), *args],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    B, R = META[name]["B"], META[name]["R"]
+    assert f"PSNR: {META[name]['psnr']}\n" in p.stdout
+    assert f"Output file dimensions: (352 x 1440)" in p.stdout and "Computation time:" in p.stdout
+    out = open(tmp_path / f"output_{B}_{R}.yuv", "rb").read()
+    assert hashlib.md5(out).hexdigest() == META[name]["yuv_md5"]
+    rows = [l.split() for l in open(tmp_path / f"mv_{B}_{R}.txt")]
+    assert len(rows) == META[name]["blocks"]
+    assert [int(r[5]) for r in rows] == FIELDS[name + "/mvx"].tolist()
+    assert [int(r[7]) for r in rows] == FIELDS[name + "/ssd"].tolist()
+    assert [int(r[8], 16) for r in rows] == FIELDS[name + "/score_bits"].tolist()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=["generic", "auto"])
+def test_device_path_bands_and_batches(orc, kernel):
+    """Device-resident entry point with torch-owned memory: batch of pairs in one
+    call, band sharding by block rows, padded pitch."""
+    torch = _torch()
+    W, H, B, R = 208, 120, 16, 32
+    pairs = [me.shifted_noise_pair(W, H, seed=s, shift=(s, -s)) for s in (1, 2, 3)]
+    exp = [orc.search(c, r, B, R) for c, r in pairs]
+    pitch = 256
+    cur = torch.zeros((3, H, pitch), dtype=torch.uint8, device="cuda")
+    ref = torch.zeros_like(cur)
+    for i, (c, r) in enumerate(pairs):
+        cur[i, :, :W] = torch.from_numpy(c).cuda()
+        ref[i, :, :W] = torch.from_numpy(r).cuda()
+    with me.Estimator(W, H, B, R, max_pairs=3, kernel=kernel) as est:
+        nb = est.num_blocks
+        mvx = torch.full((3, nb), -99, dtype=torch.int32, device="cuda")
+        mvy = torch.full_like(mvx, -99)
+        ssd = torch.zeros((3, nb), dtype=torch.int32, device="cuda")
+        score = torch.zeros((3, nb), dtype=torch.float32, device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            # two bands, as two GPUs would split one frame
+            mid = est.blocks_y // 2
+            est.search_device(cur, ref, pitch, H * pitch, 3, mvx, mvy, ssd, score, s.cuda_stream, 0, mid)
+            est.search_device(cur, ref, pitch, H * pitch, 3, mvx, mvy, ssd, score, s.cuda_stream, mid, est.blocks_y)
+        s.synchronize()
+        out = {"mvx": mvx.cpu().numpy(), "mvy": mvy.cpu().numpy(), "ssd": ssd.cpu().numpy().view(np.uint32),
+               "score": score.cpu().numpy()}
+        for p in range(3):
+            check_against(out, p, exp[p]["mvx"], exp[p]["mvy"], exp[p]["ssd"], exp[p]["score"].view(np.uint32))
+        # unaligned pitch falls back to the generic kernel but stays exact
+        if kernel == me.ME_KERNEL_AUTO:
+            cur2 = torch.zeros((H, W + 3), dtype=torch.uint8, device="cuda")
+            ref2 = torch.zeros_like(cur2)
+            cur2[:, :W] = cur[0, :, :W]
+            ref2[:, :W] = ref[0, :, :W]
+            mvx.fill_(-99)
+            est.search_device(cur2, ref2, W + 3, 0, 1, mvx, mvy, ssd, score)
+            torch.cuda.synchronize()
+            assert np.array_equal(mvx[0].cpu().numpy(), exp[0]["mvx"])
+
+
+def test_postprocess_device_matches_golden_yuv():
+    torch = _torch()
+    name = "foreman_yf4_yf1_8_12"
+    cur8, ref8 = me.foreman(4), me.foreman(1)
+    H, W = cur8.shape
+    with me.Estimator(W, H, 8, 12) as est:
+        cur, ref = torch.from_numpy(cur8).cuda(), torch.from_numpy(ref8).cuda()
+        mvx = torch.zeros(est.num_blocks, dtype=torch.int32, device="cuda")
+        mvy = torch.zeros_like(mvx)
+        est.search_device(cur, ref, W, 0, 1, mvx, mvy)
+        out5 = torch.zeros((5 * H, W), dtype=torch.uint8, device="cuda")
+        sq = torch.zeros(1, dtype=torch.int64, device="cuda")
+        mx = torch.zeros(1, dtype=torch.int32, device="cuda")
+        est.postprocess_device(cur, ref, W, mvx, mvy, out5, sq, mx)
+        torch.cuda.synchronize()
+        assert hashlib.md5(out5.cpu().numpy().tobytes()).hexdigest() == META[name]["yuv_md5"]
+        mse = float(sq.item()) / (W * H)
+        psnr = 20 * np.log10(float(mx.item())) - 10 * np.log10(mse)   # utils.c:157-162
+        assert "%.6f" % psnr == META[name]["psnr"]
+
+
+def test_pipelined_submit_wait():
+    """me_b200_submit / me_b200_wait with pinned buffers, all slots in flight."""
+    lib = me.load_library()
+    W, H, B, R = 352, 288, 8, 12
+    cur8, ref8 = me.foreman(2), me.foreman(1)
+    n = W * H
+    name = "foreman_yf2_yf1_8_12"
+    with me.Estimator(W, H, B, R, max_pairs=2) as est:
+        nb = est.num_blocks
+        bufs = []
+        for slot in range(4):
+            raw = [lib.me_b200_host_alloc(sz) for sz in (2 * n, 2 * n, 8 * nb, 8 * nb, 8 * nb, 8 * nb)]
+            assert all(raw)
+            C.memmove(raw[0], np.concatenate([cur8.ravel(), ref8.ravel()]).ctypes.data, 2 * n)
+            C.memmove(raw[1], np.concatenate([ref8.ravel(), ref8.ravel()]).ctypes.data, 2 * n)
+            est.submit_ptr(slot, raw[0], raw[1], 2, raw[2], raw[3], raw[4], raw[5])
+            bufs.append(raw)
+        with pytest.raises(me.MeError) as ei:
+            est.submit_ptr(0, bufs[0][0], bufs[0][1], 2, bufs[0][2], bufs[0][3], 0, 0)
+        assert ei.value.code == me.ME_ERR_STATE
+        for slot in range(4):
+            est.wait(slot)
+            mvx = np.ctypeslib.as_array(C.cast(bufs[slot][2], C.POINTER(C.c_int32)), (2, nb))
+            ssd = np.ctypeslib.as_array(C.cast(bufs[slot][4], C.POINTER(C.c_uint32)), (2, nb))
+            assert np.array_equal(mvx[0], FIELDS[name + "/mvx"]) and np.array_equal(ssd[0], FIELDS[name + "/ssd"])
+            assert not mvx[1].any() and not ssd[1].any()      # ref vs ref: zero motion, zero cost
+            for r in bufs[slot]:
+                lib.me_b200_host_free(r)
+        with pytest.raises(me.MeError) as ei:
+            est.wait(0)
+        assert ei.value.code == me.ME_ERR_STATE
+
+
+def recompute_ssd(cur, ref, B, mvx, mvy):
+    """SSD of the chosen candidates from the frames alone (numpy)."""
+    H, W = cur.shape
+    x0, y0, w, h = me.block_grid(W, H, B)
+    c = cur.astype(np.int64)
+    r = ref.astype(np.int64)
+    out = np.zeros(len(x0), np.int64)
+    for i in range(len(x0)):
+        a = c[y0[i]:y0[i] + h[i], x0[i]:x0[i] + w[i]]
+        b = r[y0[i] + mvy[i]:y0[i] + mvy[i] + h[i], x0[i] + mvx[i]:x0[i] + mvx[i] + w[i]]
+        out[i] = ((a - b) ** 2).sum()
+    return out
+
+
+@pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 32), (1920, 1080, 16, 64), (3840, 2160, 8, 32),
+                                     (3840, 2160, 16, 32)])
+def test_full_size_properties(orc, W, H, B, R):
+    """BASELINE.json sizes: size-independent properties + oracle on a band.
+    (a) pure translation: interior blocks recover the shift with SSD 0;
+    (b) the reported SSD equals the SSD recomputed from the frames at the reported MV;
+    (c) MVs stay inside the clamped window; (d) two top block rows and the bottom
+    block row equal the oracle bit for bit; (e) generic and tuned kernels agree."""
+    rng = np.random.Generator(np.random.PCG64(W + R))
+    base = rng.integers(0, 256, (H + 64, W + 64), dtype=np.uint8)
+    dx, dy = 7, -5
+    ref = np.ascontiguousarray(base[32:32 + H, 32:32 + W])
+    cur = np.ascontiguousarray(base[32 + dy:32 + dy + H, 32 + dx:32 + dx + W])   # cur(x,y) = ref(x+dx, y+dy)
+    cur2, ref2 = me.tiled_frames(W, H)
+    with me.Estimator(W, H, B, R, max_pairs=2) as est:
+        out = est.search_u8(np.stack([cur, cur2]), np.stack([ref, ref2]))
+        tuned = est.kernel_in_use
+    x0, y0, w, h = me.block_grid(W, H, B)
+    interior = (x0 + dx >= 0) & (y0 + dy >= 0) & (x0 + w + dx <= W) & (y0 + h + dy <= H)
+    assert np.all(out["mvx"][0][interior] == dx) and np.all(out["mvy"][0][interior] == dy)
+    assert not out["ssd"][0][interior].any()
+    for p, (c, r) in enumerate(((cur, ref), (cur2, ref2))):
+        mvx, mvy = out["mvx"][p], out["mvy"][p]
+        assert np.all(mvx >= -np.minimum(R, x0)) and np.all(mvx <= np.minimum(R, W - w - x0))
+        assert np.all(mvy >= -np.minimum(R, y0)) and np.all(mvy <= np.minimum(R, H - h - y0))
+        assert np.array_equal(recompute_ssd(c, r, B, mvx, mvy), out["ssd"][p].astype(np.int64))
+    nbx = -(-W // B)
+    nb = len(x0)
+    for (b0, b1) in ((0, 2 * nbx), (nb - nbx, nb)):
+        o = orc.search(cur2, ref2, B, R, b0, b1)
+        assert np.array_equal(out["mvx"][1][b0:b1], o["mvx"]) and np.array_equal(out["mvy"][1][b0:b1], o["mvy"])
+        assert np.array_equal(out["ssd"][1][b0:b1], o["ssd"])
+        assert np.array_equal(out["score"][1][b0:b1].view(np.uint32), o["score"].view(np.uint32))
+    if tuned == me.ME_KERNEL_TILED:
+        with me.Estimator(W, H, B, R, kernel=me.ME_KERNEL_GENERIC) as est:
+            g = est.search_u8(cur2, ref2)
+        for k in ("mvx", "mvy", "ssd"):
+            assert np.array_equal(g[k][0], out[k][1]), k
+        assert np.array_equal(g["score"][0].view(np.uint32), out["score"][1].view(np.uint32))
+
+
+def test_int_peak_microbenchmarks_run():
+    for which in (0, 1, 2):
+        rate, mhz = me.int_peak(which, iters=200)
+        assert rate > 1e12 and 500 < mhz < 3000
