@@ -1,11 +1,575 @@
-// me_tiled.cu -- tuned full-search kernel (placeholder until the first parity run).
+// me_tiled.cu -- tuned full-search kernel for sm_100a (the hot path).
+//
+// Reference being replaced: the per-block exhaustive scan of
+// src/cpu/main.c:18-82 (computeMse / findBestMatchMse / findBestBlkMse) for all
+// blocks of a batch of frame pairs (the dispatch loop main.c:144-158).
+//
+// Shape of the computation
+//   An ITEM is a run of NS horizontally adjacent STRIPS of one block row of one
+//   frame pair; a strip is NSUB adjacent blocks = 4*WORDS pixels wide.  All
+//   candidates of an item live in one macro window of (NS*4*WORDS + 2R) x
+//   (2R + BH) reference pixels.  A persistent CTA (one per SM) walks its items:
+//     * a producer warp TMA-loads (cp.async.bulk.tensor, 3-D u8 tensor map) the
+//       macro window and the current-frame strip tile into a 2-stage shared-memory
+//       ring guarded by mbarriers, then derives three more copies of the window,
+//       shifted left by 1, 2 and 3 bytes (one funnel shift per word; TMA itself
+//       only accepts 16-byte aligned inner coordinates -- measured, tools/tma_probe.cu).
+//       The byte-shifted copies are what lets every candidate read its reference
+//       row with aligned 32-bit LDS and no PRMT/SHF in the inner loop: the
+//       candidate at horizontal byte offset u reads copy u&3 at word u>>2.  Frame
+//       borders cost nothing: TMA zero-fills out-of-frame bytes and out-of-frame
+//       candidates are never scored (main.c:73-76 clamps the window).
+//     * consumer warps pull 32-task chunks from a shared-memory counter.  A TASK
+//       is (strip, horizontal offset dx, vertical part): the thread keeps the
+//       strip's current-frame rows in registers (BH x WORDS words) and STREAMS
+//       down the window column; each reference row it loads (WORDS LDS.32) is
+//       scored against all BH current rows, feeding BH live candidates whose
+//       accumulators rotate through a register file of BH slots (the period-BH
+//       loop is fully unrolled so every index is static).  Four pixels cost one
+//       VABSDIFF4.U8 (ALU pipe) + one IDP.4A.U8.U8 (FMA pipe): exact integer SSD.
+//     * a candidate that has seen its BH rows is folded into the thread's running
+//       minimum of key32 = ssd << 8 | dy.  At the end of a chunk the lanes of one
+//       block combine (MATCH.ANY + CREDUX.MIN) and one lane does a 64-bit shared
+//       atomicMin of key32 << 32 | dx.  The unsigned minimum of (ssd, dy, dx) is
+//       exactly the reference's first strict minimum in y-major/x-minor order
+//       (main.c:53-62); ssd < 2^24 makes float(ssd)/float(w*h) the reference's
+//       score bit for bit (main.c:19-27).
+//     * when every consumer warp has left an item the producer warp writes the
+//       item's motion vectors / SSD / score (SoA) and refills the stage.
+//   Vertical parts always hold m*BH + 1 candidates, so the ramp-up and ramp-down
+//   of the rotating accumulators have a static shape and are skipped with
+//   warp-uniform branches: no wasted pixel-compares, no validity tests in the loop.
+//   Parts may overlap when the clamped window height is not of that form (a
+//   duplicate candidate yields the same key, so the minimum is unchanged).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
 #include "me_device.cuh"
+
 namespace me {
-struct TiledPlan { int unused; };
-bool tiled_supported(const Geom &, size_t, size_t, const void *, const void *) { return false; }
-cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &, int) { *plan = nullptr; return cudaErrorNotSupported; }
-void tiled_plan_destroy(TiledPlan *) {}
-cudaError_t launch_tiled(TiledPlan *, const Geom &, const Frames &, int, const Out &, cudaStream_t, const char **) {
-  return cudaErrorNotSupported;
+
+namespace {
+
+constexpr int kConsumerWarps = 15;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStages = 2;
+constexpr uint32_t kNoKey = 0xffffffffu;
+
+struct TiledParams {
+  int W, H, B, R;
+  int nbx, nby;           // blocks per row / rows of the whole frame
+  int by_begin, by_count; // block rows handled by this launch
+  int npairs;
+  int strips_per_row;     // ceil(nbx / NSUB)
+  int ns;                 // strips per item
+  int items_per_row;      // ceil(strips_per_row / ns)
+  int total_items;        // items_per_row * by_count * npairs
+  int wb, wh;             // window box: bytes per row (pitch), rows
+  int copy_bytes;         // wb * wh (multiple of 128)
+  int cur_pitch;          // ns * 4 * WORDS bytes
+  int stage_bytes;        // 4 copies + cur tile + best keys, 128-aligned
+  int parts_target;       // wanted vertical parts per column
+  int e;                  // bytes between the 16-aligned TMA origin and the window origin x0-R
+  int cls_u0[4];          // first byte offset u = e + dx of class s = u & 3
+  int cls_n[4];           // number of dx offsets in that class
+  Out out;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
+                                            int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- item geometry
+struct Item {
+  int pair, by, strip0, ns;  // ns = strips actually present in this item
+  int y0;                    // top pixel row of the block row
+  int dy_lo, nc;             // first valid window-relative row offset, number of vertical candidates
+  int m, nparts;             // part length = m*BH + 1
+  int ntasks, nchunks, tpp;  // tpp = tasks per part
+};
+
+template <int BH>
+__device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
+  Item I;
+  const int per_pair = p.items_per_row * p.by_count;
+  I.pair = it / per_pair;
+  int rem = it - I.pair * per_pair;
+  const int row = rem / p.items_per_row;
+  const int ir = rem - row * p.items_per_row;
+  I.by = p.by_begin + row;
+  I.strip0 = ir * p.ns;
+  I.ns = min(p.ns, p.strips_per_row - I.strip0);
+  I.y0 = I.by * p.B;
+  // clamped window rows (main.c:74,76) as window-relative offsets dyr in [0, 2R], mvy = dyr - R
+  I.dy_lo = max(0, p.R - I.y0);
+  const int dy_hi = min(2 * p.R, p.H - BH - I.y0 + p.R);
+  I.nc = dy_hi - I.dy_lo + 1;
+  const int want = (I.nc + p.parts_target - 1) / p.parts_target;
+  I.m = min((want - 1 + BH - 1) / BH, (I.nc - 1) / BH);
+  const int L = I.m * BH + 1;
+  I.nparts = (I.nc + L - 1) / L;
+  I.tpp = I.ns * (2 * p.R + 1);
+  I.ntasks = I.tpp * I.nparts;
+  I.nchunks = (I.ntasks + 31) >> 5;
+  return I;
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int WORDS, int BH, int NSUB>
+__global__ void __launch_bounds__(kThreads, 1)
+tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
+                    const __grid_constant__ TiledParams p) {
+  constexpr int SW = 4 * WORDS;       // strip width in pixels
+  constexpr int BW = SW / NSUB;       // block width == p.B
+  constexpr int WPB = WORDS / NSUB;   // words per block row
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t tma_bar[kStages];    // TMA bytes landed (producer waits)
+  __shared__ __align__(8) uint64_t full_bar[kStages];   // shifted copies built (consumers wait)
+  __shared__ __align__(8) uint64_t empty_bar[kStages];  // all consumer warps left the item
+  __shared__ uint32_t chunk_ctr[kStages];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int best_off = 4 * p.copy_bytes + p.cur_pitch * BH;  // byte offset of the key array in a stage
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&tma_bar[s], 1);
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nblk_item = p.ns * NSUB;  // key slots per stage
+
+  if (warp == kConsumerWarps) {
+    // ===================== producer warp =====================
+    const int grid = (int)gridDim.x;
+    const int nmine = p.total_items > (int)blockIdx.x ? (p.total_items - (int)blockIdx.x + grid - 1) / grid : 0;
+    // iteration k: (B) finish the load of item k-1 (build its shifted copies, release it to the
+    // consumers), then (A) recycle the stage of item k-kStages (publish its results) and start
+    // the TMA of item k.  B before A keeps the consumers fed while A waits for them.
+    for (int k = 0; k <= nmine + kStages; k++) {
+      if (k >= 1 && k - 1 < nmine) {
+        const int stage = (k - 1) % kStages;
+        uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+        mbar_wait(&tma_bar[stage], ((k - 1) / kStages) & 1);
+        const uint32_t *c0 = reinterpret_cast<const uint32_t *>(sb);
+        uint32_t *c1 = reinterpret_cast<uint32_t *>(sb + p.copy_bytes);
+        uint32_t *c2 = reinterpret_cast<uint32_t *>(sb + 2 * (size_t)p.copy_bytes);
+        uint32_t *c3 = reinterpret_cast<uint32_t *>(sb + 3 * (size_t)p.copy_bytes);
+        const int nwords = (p.wb * p.wh) >> 2;
+        // word i of copy s = bytes [4i+s, 4i+s+4) of the window; the word after a row's last one
+        // belongs to the next row, but those bytes lie in the >= 3 byte slack of wb
+#pragma unroll 4
+        for (int i = lane; i < nwords; i += 32) {
+          const uint32_t lo = c0[i], hi = c0[i + 1];
+          c1[i] = __funnelshift_r(lo, hi, 8);
+          c2[i] = __funnelshift_r(lo, hi, 16);
+          c3[i] = __funnelshift_r(lo, hi, 24);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+      }
+      const int stage = k % kStages;
+      uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+      unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+      if (k >= kStages && k - kStages < nmine) {
+        // item k - kStages used this stage and is complete: publish its results
+        mbar_wait(&empty_bar[stage], ((k / kStages) - 1) & 1);
+        const Item D = decode_item<BH>(p, (int)blockIdx.x + (k - kStages) * grid);
+        for (int b = lane; b < D.ns * NSUB; b += 32) {
+          const int bx = D.strip0 * NSUB + b;
+          if (bx < p.nbx) {
+            const unsigned long long key = best[b];
+            const uint32_t k32 = (uint32_t)(key >> 32);
+            const uint32_t ssd = k32 >> 8;
+            const size_t oi = (size_t)D.pair * p.nbx * p.nby + (size_t)D.by * p.nbx + bx;
+            if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
+            if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
+            if (p.out.ssd) p.out.ssd[oi] = ssd;
+            if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(BW * BH));  // main.c:27
+          }
+        }
+        __syncwarp();
+      }
+      if (k < nmine) {
+        const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
+        for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
+        if (lane == 0) chunk_ctr[stage] = 0;
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
+          mbar_arrive_expect_tx(&tma_bar[stage], bytes);
+          // 16-byte aligned origin: e bytes left of the window origin x0 - R
+          tma_load_3d(sb, &map_ref, &tma_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
+          tma_load_3d(sb + 4 * (size_t)p.copy_bytes, &map_cur, &tma_bar[stage], I.strip0 * SW, I.y0, I.pair);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  int k = 0;
+  for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, k++) {
+    const int stage = k % kStages;
+    uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+    const Item I = decode_item<BH>(p, it);
+    mbar_wait(&full_bar[stage], (k / kStages) & 1);
+
+    const int L = I.m * BH + 1;
+    // tasks are ordered by byte-phase class s = (e + dx) & 3 so that a warp reads one copy
+    const int e1 = I.ns * p.cls_n[0], e2 = e1 + I.ns * p.cls_n[1], e3 = e2 + I.ns * p.cls_n[2];
+
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = (int)atomicAdd(&chunk_ctr[stage], 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= I.nchunks) break;
+
+      // ---- decode this lane's task: (part, s, strip, j); dx = 4j + s
+      int task = c * 32 + lane;
+      const bool active = task < I.ntasks;
+      task = min(task, I.ntasks - 1);
+      const int part = task / I.tpp;
+      int rem = task - part * I.tpp;
+      int s;
+      if (rem < e1) { s = 0; }
+      else if (rem < e2) { s = 1; rem -= e1; }
+      else if (rem < e3) { s = 2; rem -= e2; }
+      else { s = 3; rem -= e3; }
+      const int nj = p.cls_n[s];
+      const int st = rem / nj;
+      const int j = rem - st * nj;
+      const int u = p.cls_u0[s] + 4 * j;  // byte offset from the aligned TMA origin
+      const int dx = u - p.e;             // window-relative horizontal offset, mvx = dx - R
+      // vertical part: candidates [c0, c0 + L), evenly spread, the last one ends at nc
+      const int c0 = I.nparts > 1 ? (int)(((long long)(I.nc - L) * part) / (I.nparts - 1)) : 0;
+
+      // ---- current-frame rows of the strip into registers
+      uint32_t cur[BH][WORDS];
+      {
+        const uint4 *ct = reinterpret_cast<const uint4 *>(sb + 4 * (size_t)p.copy_bytes);
+        const int pitch4 = p.cur_pitch >> 4;
+#pragma unroll
+        for (int r = 0; r < BH; r++)
+#pragma unroll
+          for (int q = 0; q < WORDS / 4; q++) {
+            const uint4 v = ct[r * pitch4 + st * (WORDS / 4) + q];
+            cur[r][4 * q + 0] = v.x; cur[r][4 * q + 1] = v.y; cur[r][4 * q + 2] = v.z; cur[r][4 * q + 3] = v.w;
+          }
+      }
+
+      uint32_t acc[NSUB][BH];
+      uint32_t bestk[NSUB];
+#pragma unroll
+      for (int b = 0; b < NSUB; b++) bestk[b] = kNoKey;
+
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)s * p.copy_bytes +
+                                                                (size_t)(I.dy_lo + c0) * p.wb) +
+                             st * WORDS + (u >> 2);
+      const int pitchw = p.wb >> 2;
+      // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
+      int dy_fin = I.dy_lo + c0 - (BH - 1);
+
+      for (int per = 0; per <= I.m; per++) {
+        const bool first = per == 0;
+        const bool last = per == I.m;
+#pragma unroll
+        for (int s_ = 0; s_ < BH; s_++) {
+          uint32_t ref[WORDS];
+#pragma unroll
+          for (int w = 0; w < WORDS; w++) ref[w] = rowp[w];
+          rowp += pitchw;
+
+          // one (current row r) x (this reference row) group: slot (s_ - r) mod BH
+          auto group = [&](const int r) {
+            const int slot = (s_ - r + BH) % BH;
+#pragma unroll
+            for (int b = 0; b < NSUB; b++) {
+              uint32_t a = (r == 0) ? 0u : acc[b][slot];
+#pragma unroll
+              for (int w = 0; w < WPB; w++) {
+                const uint32_t d = __vabsdiffu4(cur[r][b * WPB + w], ref[b * WPB + w]);
+                a = __dp4a(d, d, a);
+              }
+              acc[b][slot] = a;
+              if (r == BH - 1) {
+                // candidate complete: fold (ssd << 8 | dy) into the running minimum
+                const uint32_t key = (a << 8) + (uint32_t)(dy_fin + s_);
+                bestk[b] = min(bestk[b], key);
+              }
+            }
+          };
+          if (!last) {
+#pragma unroll
+            for (int r = 0; r < s_; r++) group(r);
+          }
+          group(s_);
+          if (!first) {
+#pragma unroll
+            for (int r = s_ + 1; r < BH; r++) group(r);
+          }
+        }
+        dy_fin += BH;
+      }
+
+      // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
+      const int x_strip = (I.strip0 + st) * SW;
+      const unsigned peers = __match_any_sync(0xffffffffu, active ? st : -1 - lane);
+      const bool leader = (peers & (0u - peers)) == (1u << lane);
+#pragma unroll
+      for (int b = 0; b < NSUB; b++) {
+        const int x0 = x_strip + b * BW;
+        // horizontal clamp (main.c:73,75): candidate column x0 + dx - R must lie in [0, W - BW]
+        const bool ok = active && x0 < p.W && (x0 + dx - p.R >= 0) && (x0 + dx - p.R <= p.W - BW);
+        const uint32_t key = ok ? bestk[b] : kNoKey;
+        const uint32_t mkey = __reduce_min_sync(peers, key);
+        const uint32_t mdx = __reduce_min_sync(peers, key == mkey ? (uint32_t)dx : 0xffffu);
+        if (leader && mkey != kNoKey)
+          atomicMin(&best[st * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct Shape {
+  int words, bh, nsub;
+};
+
+// geometry -> kernel instantiation for FULL block rows, or {0,0,0}
+Shape shape_for(int B) {
+  if (B == 16) return Shape{4, 16, 1};
+  if (B == 8) return Shape{8, 8, 4};
+  return Shape{0, 0, 0};
+}
+
+}  // namespace
+
+struct TiledPlan {
+  int sms = 148;
+  int max_smem = 0;
+  int parts_target = 1;
+  int ns_override = 0;
+};
+
+bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
+  if (shape_for(g.B).words == 0) return false;
+  if (g.W % g.B != 0) return false;           // partial-width blocks: generic kernel
+  if (g.R < 0 || g.R > 120) return false;     // key packs dy in 8 bits; TMA box <= 256 rows
+  if (g.W < g.B || g.H < g.B) return false;
+  if ((pitch & 15) || (pair_stride & 15)) return false;
+  if (((uintptr_t)cur & 15) || ((uintptr_t)ref & 15)) return false;
+  if (!get_encode()) return false;
+  return true;
+}
+
+cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/) {
+  *plan = nullptr;
+  if (shape_for(g.B).words == 0) return cudaErrorNotSupported;
+  TiledPlan *pl = new TiledPlan();
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) {
+    delete pl;
+    return e;
+  }
+  const char *pt = getenv("ME_B200_PARTS");
+  const char *ns = getenv("ME_B200_NS");
+  pl->parts_target = pt ? atoi(pt) : 0;
+  pl->ns_override = ns ? atoi(ns) : 0;
+  *plan = pl;
+  return cudaSuccess;
+}
+
+void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
+
+namespace {
+
+template <int WORDS, int BH, int NSUB>
+cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
+                         int by_begin, int by_count, cudaStream_t s, const char **err) {
+  constexpr int SW = 4 * WORDS;
+  TiledParams p;
+  memset(&p, 0, sizeof p);
+  p.W = g.W; p.H = g.H; p.B = g.B; p.R = g.R;
+  p.nbx = g.nbx; p.nby = g.nby;
+  p.by_begin = by_begin; p.by_count = by_count;
+  p.npairs = npairs;
+  p.strips_per_row = (g.nbx + NSUB - 1) / NSUB;
+  p.wh = 2 * g.R + BH;
+  const int static_smem = 256;
+  const int ebytes = (16 - (g.R % 16)) % 16;  // SW is a multiple of 16, so every item has the same phase
+  // Choose strips per item (ns) and vertical parts per column with a small cost model:
+  // a CTA's time ~ (items it owns) x (chunks per item) x (instructions per task) / consumer warps.
+  // ns is bounded by the TMA box (<= 256 B per row) and by two stages of shared memory.
+  const long long rows_total = (long long)by_count * npairs;
+  const int nc = 2 * g.R + 1;
+  double best_cost = 1e300;
+  int best_ns = 0, best_parts = 1;
+  for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
+    const int wb = (ebytes + ns * SW + 2 * g.R + 3 + 15) & ~15;
+    if (wb > 256 || ns * SW > 256) break;
+    const int copy = ((wb * p.wh) + 127) & ~127;
+    const int stage = (4 * copy + ns * SW * BH + ns * NSUB * 8 + 127) & ~127;
+    if (kStages * stage + static_smem > plan->max_smem) break;
+    if (plan->ns_override > 0 && ns != plan->ns_override) continue;
+    const long long items = rows_total * ((p.strips_per_row + ns - 1) / ns);
+    const long long per_cta = (items + plan->sms - 1) / plan->sms;
+    for (int parts = 1; parts <= 8; parts++) {
+      if (plan->parts_target > 0 && parts != plan->parts_target) continue;
+      const int want = (nc + parts - 1) / parts;
+      int m = (want - 1 + BH - 1) / BH;
+      if (m > (nc - 1) / BH) m = (nc - 1) / BH;
+      const int L = m * BH + 1;
+      const int nparts = (nc + L - 1) / L;
+      const long long chunks = ((long long)ns * nc * nparts + 31) / 32;
+      // per task: L candidates x BH rows x WORDS x 2 int ops, plus per streamed row WORDS LDS + ~4
+      const double task = (double)L * BH * WORDS * 2.0 + (double)(L + BH - 1) * (WORDS + 4.0) + 150.0;
+      // warps flow from one item into the next, so chunks only quantise over the CTA's whole run
+      const double cost = (double)((per_cta * chunks + kConsumerWarps - 1) / kConsumerWarps) * task;
+      if (cost < best_cost * 0.999) { best_cost = cost; best_ns = ns; best_parts = parts; }
+    }
+  }
+  if (best_ns == 0) { *err = "tiled: window does not fit shared memory"; return cudaErrorInvalidConfiguration; }
+  const int ns = best_ns;
+  p.ns = ns;
+  p.parts_target = best_parts;
+  p.items_per_row = (p.strips_per_row + ns - 1) / ns;
+  p.total_items = (int)(p.items_per_row * rows_total);
+  p.wb = (ebytes + ns * SW + 2 * g.R + 3 + 15) & ~15;
+  p.e = ebytes;
+  for (int c = 0; c < 4; c++) {
+    const int u0 = ebytes + (((c - ebytes) % 4) + 4) % 4;
+    p.cls_u0[c] = u0;
+    p.cls_n[c] = u0 <= ebytes + 2 * g.R ? (ebytes + 2 * g.R - u0) / 4 + 1 : 0;
+  }
+  p.copy_bytes = ((p.wb * p.wh) + 127) & ~127;
+  p.cur_pitch = ns * SW;
+  p.stage_bytes = (4 * p.copy_bytes + p.cur_pitch * BH + ns * NSUB * 8 + 127) & ~127;
+  p.out = o;
+
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  CUtensorMap map_ref, map_cur;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)npairs};
+  const cuuint64_t strides[2] = {(cuuint64_t)f.pitch, (cuuint64_t)(npairs > 1 ? f.pair_stride : f.pitch * g.H)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t box_ref[3] = {(cuuint32_t)p.wb, (cuuint32_t)p.wh, 1};
+  const cuuint32_t box_cur[3] = {(cuuint32_t)p.cur_pitch, (cuuint32_t)BH, 1};
+  CUresult r1 = enc(&map_ref, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)f.ref, dims, strides, box_ref, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&map_cur, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)f.cur, dims, strides, box_cur, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    static char msg[96];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d, %d) wb=%d wh=%d", (int)r1, (int)r2, p.wb, p.wh);
+    *err = msg;
+    return cudaErrorInvalidValue;
+  }
+  const int smem = kStages * p.stage_bytes;
+  auto kern = tiled_search_kernel<WORDS, BH, NSUB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; return e; }
+  const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
+  kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) *err = "tiled_search_kernel launch";
+  return e;
+}
+
+}  // namespace
+
+cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
+                         cudaStream_t s, const char **err) {
+  // full-height block rows go to the shape for B; a partial bottom row (h < B) is a
+  // different block shape and runs on the generic kernel as a one-row band.
+  const int full_rows = g.H / g.B;  // rows with h == B
+  const int r0 = g.by_begin, r1 = g.by_begin + g.by_count;
+  const int t1 = r1 < full_rows ? r1 : full_rows;
+  cudaError_t e = cudaSuccess;
+  if (t1 > r0) {
+    if (g.B == 16) e = launch_shape<4, 16, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+    else if (g.B == 8) e = launch_shape<8, 8, 4>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+    else { *err = "tiled: unsupported block size"; return cudaErrorNotSupported; }
+    if (e != cudaSuccess) return e;
+  }
+  if (r1 > full_rows) {
+    Geom gb = g;
+    gb.by_begin = r0 > full_rows ? r0 : full_rows;
+    gb.by_count = r1 - gb.by_begin;
+    e = launch_generic(gb, f, npairs, o, s);
+    if (e != cudaSuccess) *err = "launch_generic(partial bottom row)";
+  }
+  return e;
+}
+
 }  // namespace me
