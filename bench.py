@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the full-search path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A STEP is one pass of the hot path (the replacement of src/cpu/main.c:144-158)
+over one batch of synthetic frame pairs.  Default workload = BASELINE.json
+configs[1]: 1920x1080 luma, 16x16 blocks, full search +-32 (Beauty is absent from
+the reference checkout, so the frames are the seeded synthetic stand-in of
+SURVEY.md section 8d).  One process per GPU (torchrun for N > 1), pairs sharded by
+rank, no data-path collective (frame pairs are independent) => weak scaling.
+
+Printed JSON line (rank 0):
+  value     frames/s, whole job, inputs resident in HBM, CUDA events on the launch stream,
+            barrier + synchronize on both sides, max over ranks
+  e2e       same metric through the host-buffer C ABI (me_b200_submit / me_b200_wait):
+            pinned host frames -> H2D -> search -> D2H of the motion field, every step
+  roofline  integer-pipe roofline of the search kernel: algorithmic lane-instructions
+            (0.5 per pixel-compare: VABSDIFF4 + IDP.4A per 4 pixels) / step time,
+            against the VABSDIFF4+IDP.4A pair rate measured live by me_b200_int_peak
+  cpu_baseline  the unmodified reference CPU path (oracle/_ref) on this box's host cores
+--impl reference times the reference's own CPU implementation instead (no GPU work).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, B, R, pairs per GPU per step, description)
+    "1080p_16x16_pm32": (1920, 1080, 16, 32, 64, "BASELINE configs[1]: synthetic 1920x1080 luma, 16x16 blocks, full search +-32"),
+    "1080p_16x16_pm64": (1920, 1080, 16, 64, 32, "BASELINE configs[2]: synthetic 1920x1080 luma, 16x16 blocks, full search +-64"),
+    "4k_8x8_pm32": (3840, 2160, 8, 32, 16, "BASELINE configs[4]: synthetic 3840x2160 luma, 8x8 blocks, full search +-32"),
+    "4k_16x16_pm32": (3840, 2160, 16, 32, 16, "BASELINE configs[4]: synthetic 3840x2160 luma, 16x16 blocks, full search +-32"),
+    "foreman_8x8_pm12": (352, 288, 8, 12, 512, "BASELINE configs[0]: Foreman YF2->YF1, reference defaults 8x8 +-12"),
+}
+METRIC = "1080p_frames_per_sec_full_search_pm32"
+
+
+def make_batch(name, pairs, rank):
+    """Deterministic synthetic batch (pairs, H, W) uint8 x2; a different seed per pair and rank."""
+    import motionestimation_b200 as me
+    W, H, B, R, _, _ = WORKLOADS[name]
+    if name.startswith("foreman"):
+        c, r = me.foreman(2), me.foreman(1)
+        return np.stack([c] * pairs), np.stack([r] * pairs)
+    # a few distinct pairs, repeated: tiled Foreman (real texture/motion) + shifted noise
+    base = [me.tiled_frames(W, H, 2, 1), me.tiled_frames(W, H, 4, 1),
+            me.shifted_noise_pair(W, H, seed=1234 + rank), me.shifted_noise_pair(W, H, seed=99 + rank, shift=(-11, 7))]
+    cur = np.stack([base[i % len(base)][0] for i in range(pairs)])
+    ref = np.stack([base[i % len(base)][1] for i in range(pairs)])
+    return cur, ref
+
+
+class ClockSampler(threading.Thread):
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md recipe),
+    read through NVML every few ms (nvidia-smi itself is too slow for sub-second regions)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.max_mhz, self.err = index, [], False, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when mapping the torch index to an NVML index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((float(mhz), int(reasons), watts))
+                time.sleep(0.004)
+        except Exception as ex:  # pragma: no cover
+            self.err = repr(ex)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: %s" % self.err]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
+        seen = 0
+        for r in self.rows:
+            seen |= r[1]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows),
+                "reasons": [n for n, b in bits.items() if seen & b]}
+
+
+def load_ref():
+    """oracle/_ref (the unmodified reference, prebuilt) -- test/baseline infrastructure."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import Ref, Oracle
+    if Ref.available():
+        return Ref(), "reference"
+    return Oracle(), "port"
+
+
+def cpu_reference_rate(name, budget_s, steps=1, warmup=0):
+    """Time the reference CPU search (its own thread-pool dispatch, main.c:144-158, 100 threads)
+    on a bounded sample of the workload: whole block rows from the middle of the first pair.
+    Returns (frames/s, blocks/s, dict describing the sample)."""
+    W, H, B, R, _, _ = WORKLOADS[name]
+    cur, ref = make_batch(name, 1, 0)
+    cur, ref = cur[0], ref[0]
+    lib, kind = load_ref()
+    nbx, nby = -(-W // B), -(-H // B)
+    nb = nbx * nby
+
+    def run(b0, b1):
+        if kind == "reference":
+            sec, _ = lib.search_pool(cur, ref, B, R, b0, b1, pool_threads=100)
+            return sec
+        t0 = time.perf_counter()
+        lib.search(cur, ref, B, R, b0, b1, nthreads=os.cpu_count())
+        return time.perf_counter() - t0
+
+    # probe with two interior block rows, then size the sample to the time budget
+    mid = (nby // 2) * nbx
+    t_probe = run(mid, min(nb, mid + 2 * nbx))
+    per_row = t_probe / 2
+    rows = int(max(1, min(nby, budget_s / max(per_row, 1e-6) / max(1, steps + warmup))))
+    if rows >= nby:
+        b0, b1, rows = 0, nb, nby
+    else:
+        r0 = max(0, nby // 2 - rows // 2)
+        b0, b1 = r0 * nbx, (r0 + rows) * nbx
+    for _ in range(warmup):
+        run(b0, b1)
+    ts = [run(b0, b1) for _ in range(steps)]
+    t = float(np.mean(ts))
+    blocks_s = (b1 - b0) / t
+    cores = os.cpu_count() or 1
+    return blocks_s / nb, blocks_s, {
+        "kind": kind, "cores": cores, "threads": 100 if kind == "reference" else cores,
+        "sample": f"{rows} of {nby} block rows ({b1 - b0} blocks) of one {W}x{H} pair, B={B} R={R}, "
+                  f"{steps} timed run(s) of {t * 1e3:.0f} ms; reference thread pool of 100 (main.c:144), "
+                  f"built -O2 from the unmodified sources (src/cpu/run.sh:4 uses no -O)",
+        "ms_per_step": t * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    W, H, B, R, pairs, desc = WORKLOADS[name]
+    fps, blocks_s, info = cpu_reference_rate(name, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC if name == "1080p_16x16_pm32" else name + "_frames_per_sec",
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "desc": desc, "width": W, "height": H, "blk_dim": B, "extra_span": R},
+        "blocks_per_s": blocks_s,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1080p_16x16_pm32", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import motionestimation_b200 as me
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the search has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+
+    name = args.workload
+    W, H, B, R, pairs, desc = WORKLOADS[name]
+    if args.pairs > 0:
+        pairs = args.pairs
+    pitch = (W + 15) & ~15
+    cur_np, ref_np = make_batch(name, pairs, rank)
+
+    slot_pairs = max(1, pairs // me.lib.ME_B200_MAX_SLOTS)
+    est = me.Estimator(W, H, B, R, device=local, max_pairs=slot_pairs)
+    nb = est.num_blocks
+    pc_pair = est.pixel_compares
+
+    # ---- device-resident arm -------------------------------------------------------------
+    d_cur = torch.zeros((pairs, H, pitch), dtype=torch.uint8, device="cuda")
+    d_ref = torch.zeros_like(d_cur)
+    d_cur[:, :, :W] = torch.from_numpy(cur_np).cuda()
+    d_ref[:, :, :W] = torch.from_numpy(ref_np).cuda()
+    d_mvx = torch.zeros((pairs, nb), dtype=torch.int32, device="cuda")
+    d_mvy = torch.zeros_like(d_mvx)
+    d_ssd = torch.zeros_like(d_mvx)
+    d_score = torch.zeros((pairs, nb), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    in_bytes = 2 * pairs * H * pitch
+    # L2 hygiene: either the step's inputs exceed L2 (126 MB) or we flush it between steps
+    flush = None
+    if in_bytes < 160 * 1024 * 1024:
+        flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step():
+        est.search_device(d_cur, d_ref, pitch, H * pitch, pairs, d_mvx, d_mvy, d_ssd, d_score,
+                          stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = est.launch_count
+    evs = []
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    launches = est.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = float(sum(step_ms))                      # device time of the K steps on this rank
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    fps = world * pairs * args.steps / (dev_ms_max * 1e-3)
+
+    mvx0 = d_mvx[0].cpu().numpy()   # compared with the end-to-end arm below
+
+    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ---
+    lib = me.load_library()
+    n = W * H
+    h_cur = torch.from_numpy(cur_np.reshape(pairs, n)).pin_memory()
+    h_ref = torch.from_numpy(ref_np.reshape(pairs, n)).pin_memory()
+    h_mvx = torch.zeros((pairs, nb), dtype=torch.int32).pin_memory()
+    h_mvy = torch.zeros_like(h_mvx).pin_memory()
+    h_ssd = torch.zeros_like(h_mvx).pin_memory()
+    nslots = min(me.lib.ME_B200_MAX_SLOTS, pairs // slot_pairs)
+
+    def e2e_step():
+        inflight = [False] * nslots
+        done, k = 0, 0
+        while done < pairs:
+            s = k % nslots
+            if inflight[s]:
+                est.wait(s)
+            npp = min(slot_pairs, pairs - done)
+            est.submit_ptr(s, h_cur[done].data_ptr(), h_ref[done].data_ptr(), npp, h_mvx[done].data_ptr(),
+                           h_mvy[done].data_ptr(), h_ssd[done].data_ptr(), 0)
+            inflight[s] = True
+            done += npp
+            k += 1
+        for s in range(nslots):
+            if inflight[s]:
+                est.wait(s)
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = world * pairs * args.steps / float(t.item())
+    assert np.array_equal(h_mvx[0].numpy(), mvx0), "e2e and device-resident paths disagree"
+
+    if rank == 0:
+        # ---- roofline of the search kernel (integer pipes) -----------------
+        pair_rate, mhz = 0.0, 0.0
+        for _ in range(3):
+            r_, m_ = me.int_peak(2, iters=4000, device=local)    # VABSDIFF4 + IDP.4A pairs
+            if r_ > pair_rate:
+                pair_rate, mhz = r_, m_
+        step_s = dev_ms / args.steps * 1e-3
+        lane_instr = 0.5 * pc_pair * pairs                       # algorithmic: 2 ops per 4 pixels
+        achieved = lane_instr / step_s
+        alg_bytes = pairs * (2 * W * H + 16 * nb)                # u8 cur + ref read once, 16 B/block out
+        clocks = sampler.summary()
+        line = {
+            "metric": METRIC if name == "1080p_16x16_pm32" else name + "_frames_per_sec",
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": name, "desc": desc, "width": W, "height": H, "blk_dim": B, "extra_span": R,
+                       "pairs_per_gpu_per_step": pairs, "blocks_per_pair": nb,
+                       "pixel_compares_per_pair": pc_pair, "parallelism": f"frame-pair sharding x{world}",
+                       "l2": "inputs larger than L2" if flush is None else "L2 flushed between steps (192 MB write)",
+                       "kernel": {1: "generic", 2: "tiled"}[est.kernel_in_use]},
+            "blocks_per_s": fps * nb, "pixel_compares_per_s": fps * pc_pair,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 2 * pairs * n,
+                    "d2h_bytes_per_step": 3 * pairs * nb * 4,
+                    "api": "me_b200_submit/me_b200_wait, pinned u8 host frames, %d slots x %d pairs" % (nslots, slot_pairs)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": pair_rate / 1e12,
+                         "unit": "T lane-instr/s", "frac": achieved / pair_rate if pair_rate else None,
+                         "traffic": None,
+                         "peak_source": "measured live: me_b200_int_peak(VABSDIFF4+IDP.4A pairs) at %.0f MHz" % mhz,
+                         "frac_of_single_pipe_peak": achieved / (pair_rate / 2) if pair_rate else None,
+                         "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": 6455.9,
+                                 "algorithmic_bytes_per_step": alg_bytes}},
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline:
+            cfps, cblocks, info = cpu_reference_rate(name, budget_s=15.0)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": info["cores"],
+                                    "kind": info["kind"], "sample": info["sample"], "blocks_per_s": cblocks}
+        print(json.dumps(line), flush=True)
+    est.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
