@@ -25,8 +25,16 @@
 //       down the window column; each reference row it loads (WORDS LDS.32) is
 //       scored against all BH current rows, feeding BH live candidates whose
 //       accumulators rotate through a register file of BH slots (the period-BH
-//       loop is fully unrolled so every index is static).  Four pixels cost one
-//       VABSDIFF4.U8 (ALU pipe) + one IDP.4A.U8.U8 (FMA pipe): exact integer SSD.
+//       loop is fully unrolled so every index is static).  Two exact integer
+//       formulations of the SSD are compiled (template FORM):
+//         FORM 1 (default)  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref: one IDP.4A.U8.U8
+//                per 4 pixels for the cross term; sum ref^2 over the candidate's rows is a
+//                sliding sum of per-row IDP.4A(ref,ref), sum cur^2 is per task.  Half the
+//                instructions of FORM 0 (the unrolled loop fits the instruction cache),
+//                FMA-pipe bound, and zero-padded current rows/columns make partial edge
+//                blocks free (their reference pixels are masked out of sum ref^2).
+//         FORM 0  |cur-ref| then square: VABSDIFF4.U8 (ALU pipe) + IDP.4A.U8.U8 (FMA pipe)
+//                per 4 pixels; kept for A/B measurements (env ME_B200_FORM=0), full blocks only.
 //     * a candidate that has seen its BH rows is folded into the thread's running
 //       minimum of key32 = ssd << 8 | dy.  At the end of a chunk the lanes of one
 //       block combine (MATCH.ANY + CREDUX.MIN) and one lane does a 64-bit shared
@@ -72,6 +80,7 @@ struct TiledParams {
   int cur_pitch;          // ns * 4 * WORDS bytes
   int stage_bytes;        // 4 copies + cur tile + best keys, 128-aligned
   int parts_target;       // wanted vertical parts per column
+  int partial_w;          // W % strip width != 0: reference bytes right of the frame are masked
   int e;                  // bytes between the 16-aligned TMA origin and the window origin x0-R
   int cls_u0[4];          // first byte offset u = e + dx of class s = u & 3
   int cls_n[4];           // number of dx offsets in that class
@@ -121,7 +130,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // ---------------------------------------------------------------- item geometry
 struct Item {
   int pair, by, strip0, ns;  // ns = strips actually present in this item
-  int y0;                    // top pixel row of the block row
+  int y0, h;                 // top pixel row of the block row, block height (BH or BH/2)
   int dy_lo, nc;             // first valid window-relative row offset, number of vertical candidates
   int m, nparts;             // part length = m*BH + 1
   int ntasks, nchunks, tpp;  // tpp = tasks per part
@@ -139,9 +148,10 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
   I.strip0 = ir * p.ns;
   I.ns = min(p.ns, p.strips_per_row - I.strip0);
   I.y0 = I.by * p.B;
+  I.h = min(BH, p.H - I.y0);
   // clamped window rows (main.c:74,76) as window-relative offsets dyr in [0, 2R], mvy = dyr - R
   I.dy_lo = max(0, p.R - I.y0);
-  const int dy_hi = min(2 * p.R, p.H - BH - I.y0 + p.R);
+  const int dy_hi = min(2 * p.R, p.H - I.h - I.y0 + p.R);
   I.nc = dy_hi - I.dy_lo + 1;
   const int want = (I.nc + p.parts_target - 1) / p.parts_target;
   I.m = min((want - 1 + BH - 1) / BH, (I.nc - 1) / BH);
@@ -154,7 +164,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int WORDS, int BH, int NSUB>
+template <int WORDS, int BH, int NSUB, int FORM>
 __global__ void __launch_bounds__(kThreads, 1)
 tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
                     const __grid_constant__ TiledParams p) {
@@ -229,7 +239,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
             if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
             if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
             if (p.out.ssd) p.out.ssd[oi] = ssd;
-            if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(BW * BH));  // main.c:27
+            const int bw = min(BW, p.W - bx * BW);
+            if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(bw * D.h));  // main.c:27
           }
         }
         __syncwarp();
@@ -313,8 +324,33 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
                                                                 (size_t)(I.dy_lo + c0) * p.wb) +
                              st * WORDS + (u >> 2);
       const int pitchw = p.wb >> 2;
+      const int x_strip = (I.strip0 + st) * SW;
       // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
       int dy_fin = I.dy_lo + c0 - (BH - 1);
+
+      // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
+      uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
+      const bool half = I.h != BH;          // bottom block row of height BH/2
+      const bool pw = p.partial_w != 0;
+      if (FORM == 1) {
+#pragma unroll
+        for (int b = 0; b < NSUB; b++) {
+          uint32_t a = 0;
+#pragma unroll
+          for (int r = 0; r < BH; r++)
+#pragma unroll
+            for (int w = 0; w < WPB; w++) a = __dp4a(cur[r][b * WPB + w], cur[r][b * WPB + w], a);
+          srun[b] = a;
+#pragma unroll
+          for (int r = 0; r < BH; r++) qh[b][r] = 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) {
+          // bytes of word w that lie inside the frame for the block at x_strip (columns < W)
+          const int left = p.W - (x_strip + 4 * w);
+          msk[w] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        }
+      }
 
       for (int per = 0; per <= I.m; per++) {
         const bool first = per == 0;
@@ -326,6 +362,25 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           for (int w = 0; w < WORDS; w++) ref[w] = rowp[w];
           rowp += pitchw;
 
+          if (FORM == 1) {
+            // energy of this reference row over each block's columns, then slide the window:
+            // full height: + q(t) - q(t-BH);  half height: + q(t-BH/2) - q(t-BH)
+#pragma unroll
+            for (int b = 0; b < NSUB; b++) {
+              uint32_t qt = 0;
+              if (pw) {
+#pragma unroll
+                for (int w = 0; w < WPB; w++) qt = __dp4a(ref[b * WPB + w] & msk[b * WPB + w], ref[b * WPB + w], qt);
+              } else {
+#pragma unroll
+                for (int w = 0; w < WPB; w++) qt = __dp4a(ref[b * WPB + w], ref[b * WPB + w], qt);
+              }
+              const uint32_t add = half ? qh[b][(s_ + BH / 2) % BH] : qt;
+              srun[b] = srun[b] + add - qh[b][s_];
+              qh[b][s_] = qt;
+            }
+          }
+
           // one (current row r) x (this reference row) group: slot (s_ - r) mod BH
           auto group = [&](const int r) {
             const int slot = (s_ - r + BH) % BH;
@@ -334,13 +389,18 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
               uint32_t a = (r == 0) ? 0u : acc[b][slot];
 #pragma unroll
               for (int w = 0; w < WPB; w++) {
-                const uint32_t d = __vabsdiffu4(cur[r][b * WPB + w], ref[b * WPB + w]);
-                a = __dp4a(d, d, a);
+                if (FORM == 1) {
+                  a = __dp4a(cur[r][b * WPB + w], ref[b * WPB + w], a);
+                } else {
+                  const uint32_t d = __vabsdiffu4(cur[r][b * WPB + w], ref[b * WPB + w]);
+                  a = __dp4a(d, d, a);
+                }
               }
               acc[b][slot] = a;
               if (r == BH - 1) {
                 // candidate complete: fold (ssd << 8 | dy) into the running minimum
-                const uint32_t key = (a << 8) + (uint32_t)(dy_fin + s_);
+                const uint32_t ssd = FORM == 1 ? srun[b] - 2u * a : a;
+                const uint32_t key = (ssd << 8) + (uint32_t)(dy_fin + s_);
                 bestk[b] = min(bestk[b], key);
               }
             }
@@ -359,14 +419,14 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
-      const int x_strip = (I.strip0 + st) * SW;
       const unsigned peers = __match_any_sync(0xffffffffu, active ? st : -1 - lane);
       const bool leader = (peers & (0u - peers)) == (1u << lane);
 #pragma unroll
       for (int b = 0; b < NSUB; b++) {
         const int x0 = x_strip + b * BW;
-        // horizontal clamp (main.c:73,75): candidate column x0 + dx - R must lie in [0, W - BW]
-        const bool ok = active && x0 < p.W && (x0 + dx - p.R >= 0) && (x0 + dx - p.R <= p.W - BW);
+        // horizontal clamp (main.c:73,75): candidate column x0 + dx - R must lie in [0, W - w]
+        const int bw = min(BW, p.W - x0);
+        const bool ok = active && x0 < p.W && (x0 + dx - p.R >= 0) && (x0 + dx - p.R <= p.W - bw);
         const uint32_t key = ok ? bestk[b] : kNoKey;
         const uint32_t mkey = __reduce_min_sync(peers, key);
         const uint32_t mdx = __reduce_min_sync(peers, key == mkey ? (uint32_t)dx : 0xffffu);
@@ -397,32 +457,30 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct Shape {
-  int words, bh, nsub;
-};
-
-// geometry -> kernel instantiation for FULL block rows, or {0,0,0}
-Shape shape_for(int B) {
-  if (B == 16) return Shape{4, 16, 1};
-  if (B == 8) return Shape{8, 8, 4};
-  return Shape{0, 0, 0};
-}
+// block size -> kernel shape (WORDS, BH, NSUB) per formulation, or unsupported
+bool shape_ok(int B) { return B == 16 || B == 8; }
 
 }  // namespace
 
 struct TiledPlan {
   int sms = 148;
   int max_smem = 0;
-  int parts_target = 1;
+  int parts_target = 0;
   int ns_override = 0;
+  int form = 1;  // 1: dot-product expansion (default), 0: |a-b|^2 (env ME_B200_FORM=0)
 };
 
+static int env_form() {
+  const char *f = getenv("ME_B200_FORM");
+  return (f && f[0] == '0') ? 0 : 1;
+}
+
 bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
-  if (shape_for(g.B).words == 0) return false;
-  if (g.W % g.B != 0) return false;           // partial-width blocks: generic kernel
+  if (!shape_ok(g.B)) return false;
+  if (env_form() == 0 && g.W % g.B != 0) return false;  // FORM 0 has no partial-width blocks
   if (g.R < 0 || g.R > 120) return false;     // key packs dy in 8 bits; TMA box <= 256 rows
   if (g.W < g.B || g.H < g.B) return false;
-  if ((pitch & 15) || (pair_stride & 15)) return false;
+  if ((pitch & 15) || (pair_stride & 15)) return false;  // TMA: 16-byte aligned base and strides
   if (((uintptr_t)cur & 15) || ((uintptr_t)ref & 15)) return false;
   if (!get_encode()) return false;
   return true;
@@ -430,8 +488,9 @@ bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void
 
 cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/) {
   *plan = nullptr;
-  if (shape_for(g.B).words == 0) return cudaErrorNotSupported;
+  if (!shape_ok(g.B)) return cudaErrorNotSupported;
   TiledPlan *pl = new TiledPlan();
+  pl->form = env_form();
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
@@ -452,7 +511,7 @@ void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
 
 namespace {
 
-template <int WORDS, int BH, int NSUB>
+template <int WORDS, int BH, int NSUB, int FORM>
 cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          int by_begin, int by_count, cudaStream_t s, const char **err) {
   constexpr int SW = 4 * WORDS;
@@ -513,6 +572,7 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
   p.copy_bytes = ((p.wb * p.wh) + 127) & ~127;
   p.cur_pitch = ns * SW;
   p.stage_bytes = (4 * p.copy_bytes + p.cur_pitch * BH + ns * NSUB * 8 + 127) & ~127;
+  p.partial_w = (g.W % SW) != 0;
   p.out = o;
 
   EncodeTiledFn enc = get_encode();
@@ -536,7 +596,7 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
     return cudaErrorInvalidValue;
   }
   const int smem = kStages * p.stage_bytes;
-  auto kern = tiled_search_kernel<WORDS, BH, NSUB>;
+  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; return e; }
   const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
@@ -550,21 +610,28 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
 
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err) {
-  // full-height block rows go to the shape for B; a partial bottom row (h < B) is a
-  // different block shape and runs on the generic kernel as a one-row band.
-  const int full_rows = g.H / g.B;  // rows with h == B
+  // Block rows of full height, and (FORM 1) a bottom row of exactly half height, run tiled;
+  // any other partial bottom row is a different block shape and runs on the generic kernel
+  // as a one-row band.
+  const int full_rows = g.H / g.B;
+  const int hrem = g.H % g.B;
+  const int tiled_rows = full_rows + ((plan->form == 1 && hrem == g.B / 2) ? 1 : 0);
   const int r0 = g.by_begin, r1 = g.by_begin + g.by_count;
-  const int t1 = r1 < full_rows ? r1 : full_rows;
+  const int t1 = r1 < tiled_rows ? r1 : tiled_rows;
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
-    if (g.B == 16) e = launch_shape<4, 16, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
-    else if (g.B == 8) e = launch_shape<8, 8, 4>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
-    else { *err = "tiled: unsupported block size"; return cudaErrorNotSupported; }
+    if (plan->form == 1) {
+      if (g.B == 16) e = launch_shape<4, 16, 1, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+      else e = launch_shape<4, 8, 2, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+    } else {
+      if (g.B == 16) e = launch_shape<4, 16, 1, 0>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+      else e = launch_shape<8, 8, 4, 0>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+    }
     if (e != cudaSuccess) return e;
   }
-  if (r1 > full_rows) {
+  if (r1 > tiled_rows) {
     Geom gb = g;
-    gb.by_begin = r0 > full_rows ? r0 : full_rows;
+    gb.by_begin = r0 > tiled_rows ? r0 : tiled_rows;
     gb.by_count = r1 - gb.by_begin;
     e = launch_generic(gb, f, npairs, o, s);
     if (e != cudaSuccess) *err = "launch_generic(partial bottom row)";
