@@ -158,7 +158,8 @@ int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
 #define ME_PEAK_VIMNMX       6
 #define ME_PEAK_SSD_PAIR_LDS 7 /* pairs + 1 LDS.32 per 16 pairs          */
 #define ME_PEAK_IDP4A_IADD3  8 /* IDP.4A + IADD3 1:1 (do the two pipes overlap?) */
-#define ME_PEAK_COUNT        9
+#define ME_PEAK_LOOP_REPLICA 9 /* the search kernel's register pattern: IDP.4A lanes/s */
+#define ME_PEAK_COUNT        10
 double me_b200_int_peak(int device, int which, int iters, double *sm_clock_mhz);
 
 #ifdef __cplusplus

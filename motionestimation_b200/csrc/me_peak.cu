@@ -5,6 +5,7 @@
 // independent dependency chains per thread so the pipes, not latency, bound it.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "me_b200.h"
 
 namespace {
@@ -44,7 +45,7 @@ __device__ __forceinline__ void step(uint32_t (&a)[kChains], uint32_t (&b)[kChai
 }
 
 template <int WHICH>
-__global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, int iters, uint32_t seed,
+__global__ void __launch_bounds__(512) peak_kernel(uint32_t *out, int iters, uint32_t seed,
                                                    unsigned long long *clk) {
   __shared__ uint32_t lds[1024];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) lds[i] = (i * 2654435761u) >> 31;
@@ -79,12 +80,93 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, int iters, uin
   if (r == 0x12345679u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// Replica of the search kernel's hot loop without memory traffic or branches: 64 "current"
+// registers, 16 rotating accumulators, 4 "reference" registers refreshed by one LOP3 each per
+// row step, 64 IDP.4A per step in the same register pattern.  Measures what the FMA pipe
+// sustains for that operand pattern at the search kernel's occupancy.
+__global__ void __launch_bounds__(512, 1) replica_kernel(uint32_t *out, int iters, uint32_t seed,
+                                                         unsigned long long *clk) {
+  uint32_t cur[16][4], acc[16], ref[4];
+#pragma unroll
+  for (int r = 0; r < 16; r++)
+#pragma unroll
+    for (int w = 0; w < 4; w++) cur[r][w] = seed * (r * 4 + w + 1) + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 16; r++) acc[r] = 0;
+#pragma unroll
+  for (int w = 0; w < 4; w++) ref[w] = seed ^ (threadIdx.x * (w + 7));
+  unsigned long long t0 = 0, g0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    t0 = clock64();
+  }
+  uint32_t best = 0xffffffffu;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int s_ = 0; s_ < 16; s_++) {
+#pragma unroll
+      for (int w = 0; w < 4; w++) ref[w] = (ref[w] ^ best) + 0x01010101u * (w + 1);
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const int slot = (s_ - r + 16) % 16;
+        uint32_t a = r == 0 ? 0u : acc[slot];
+#pragma unroll
+        for (int w = 0; w < 4; w++) a = __dp4a(cur[r][w], ref[w], a);
+        acc[slot] = a;
+        if (r == 15) best = min(best, (a << 8) + (uint32_t)s_);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t1 = clock64(), g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    clk[0] = t1 - t0;
+    clk[1] = g1 - g0;
+  }
+  if (best == 0x12345679u) out[blockIdx.x * blockDim.x + threadIdx.x] = best;
+}
+
+double run_replica(int iters, double *mhz) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0.0;
+  const int ctas = sms, threads = 512;
+  uint32_t *out = nullptr;
+  unsigned long long *clk = nullptr;
+  if (cudaMalloc(&out, (size_t)ctas * threads * 4) != cudaSuccess) return 0.0;
+  if (cudaMalloc(&clk, 16) != cudaSuccess) { cudaFree(out); return 0.0; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  replica_kernel<<<ctas, threads>>>(out, iters / 8 + 1, 12345u, clk);
+  cudaEventRecord(e0);
+  replica_kernel<<<ctas, threads>>>(out, iters, 12345u, clk);
+  cudaEventRecord(e1);
+  double rate = 0.0;
+  if (cudaEventSynchronize(e1) == cudaSuccess) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    unsigned long long h[2] = {0, 0};
+    cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost);
+    if (mhz) *mhz = h[1] ? (double)h[0] / (double)h[1] * 1000.0 : 0.0;
+    rate = (double)ctas * threads * (double)iters * 16 * 64 / (ms * 1e-3);  // IDP.4A lane-instructions / s
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaFree(clk);
+  return rate;
+}
+
 template <int WHICH>
 double run_peak(int iters, double *mhz) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0.0;
-  const int ctas = sms * 8, threads = 256;
+  // default: 8 CTAs x 256 threads per SM (64 warps/SM); env overrides let the bench probe the
+  // search kernel's own occupancy (1 CTA x 512 threads)
+  const char *ec = getenv("ME_PEAK_CTAS_PER_SM"), *et = getenv("ME_PEAK_THREADS");
+  const int ctas = sms * (ec ? atoi(ec) : 8), threads = et ? atoi(et) : 256;
   uint32_t *out = nullptr;
   unsigned long long *clk = nullptr;
   if (cudaMalloc(&out, (size_t)ctas * threads * 4) != cudaSuccess) return 0.0;
@@ -133,6 +215,7 @@ extern "C" double me_b200_int_peak(int device, int which, int iters, double *sm_
     case ME_PEAK_VIMNMX: return run_peak<ME_PEAK_VIMNMX>(iters, sm_clock_mhz);
     case ME_PEAK_SSD_PAIR_LDS: return run_peak<ME_PEAK_SSD_PAIR_LDS>(iters, sm_clock_mhz);
     case ME_PEAK_IDP4A_IADD3: return run_peak<ME_PEAK_IDP4A_IADD3>(iters, sm_clock_mhz);
+    case ME_PEAK_LOOP_REPLICA: return run_replica(iters / 16 + 1, sm_clock_mhz);
     default: return 0.0;
   }
 }

@@ -8,22 +8,20 @@
 //   An ITEM is a run of NS horizontally adjacent STRIPS of one block row of one
 //   frame pair; a strip is NSUB adjacent blocks = 4*WORDS pixels wide.  All
 //   candidates of an item live in one macro window of (NS*4*WORDS + 2R) x
-//   (2R + BH) reference pixels.  A persistent CTA (one per SM) walks its items:
-//     * a producer warp TMA-loads (cp.async.bulk.tensor, 3-D u8 tensor map) the
-//       macro window and the current-frame strip tile into a 2-stage shared-memory
-//       ring guarded by mbarriers, then derives three more copies of the window,
-//       shifted left by 1, 2 and 3 bytes (one funnel shift per word; TMA itself
-//       only accepts 16-byte aligned inner coordinates -- measured, tools/tma_probe.cu).
-//       The byte-shifted copies are what lets every candidate read its reference
-//       row with aligned 32-bit LDS and no PRMT/SHF in the inner loop: the
-//       candidate at horizontal byte offset u reads copy u&3 at word u>>2.  Frame
-//       borders cost nothing: TMA zero-fills out-of-frame bytes and out-of-frame
-//       candidates are never scored (main.c:73-76 clamps the window).
-//     * consumer warps pull 32-task chunks from a shared-memory counter.  A TASK
-//       is (strip, horizontal offset dx, vertical part): the thread keeps the
-//       strip's current-frame rows in registers (BH x WORDS words) and STREAMS
-//       down the window column; each reference row it loads (WORDS LDS.32) is
-//       scored against all BH current rows, feeding BH live candidates whose
+//   (2R + BH) reference pixels.  A persistent CTA (one per SM, 16 warps, no
+//   dedicated producer) walks its items through a 2..4 stage shared-memory ring:
+//     * the macro window and the current-frame strip tile of an item arrive by TMA
+//       (cp.async.bulk.tensor, 3-D u8 tensor maps, one mbarrier per stage).  TMA only
+//       accepts 16-byte aligned inner coordinates (measured, tools/tma_probe.cu), so
+//       the tile starts at the aligned column left of x0-R; frame borders cost
+//       nothing: out-of-frame bytes are zero-filled and out-of-frame candidates are
+//       never scored (main.c:73-76 clamps the window).
+//     * warps pull 32-task chunks from a per-stage shared-memory counter.  A TASK is
+//       (strip, horizontal offset dx, vertical part): the thread keeps the strip's
+//       current-frame rows in registers (BH x WORDS words) and STREAMS down the
+//       window column; each reference row (WORDS+1 aligned LDS.32, byte-aligned to
+//       the candidate column by WORDS funnel shifts on the otherwise idle ALU pipe)
+//       is scored against all BH current rows, feeding BH live candidates whose
 //       accumulators rotate through a register file of BH slots (the period-BH
 //       loop is fully unrolled so every index is static).  Two exact integer
 //       formulations of the SSD are compiled (template FORM):
@@ -42,8 +40,8 @@
 //       exactly the reference's first strict minimum in y-major/x-minor order
 //       (main.c:53-62); ssd < 2^24 makes float(ssd)/float(w*h) the reference's
 //       score bit for bit (main.c:19-27).
-//     * when every consumer warp has left an item the producer warp writes the
-//       item's motion vectors / SSD / score (SoA) and refills the stage.
+//     * the last warp to leave an item writes the item's motion vectors / SSD /
+//       score (SoA) and re-arms the stage with the TMA of the item `stages` ahead.
 //   Vertical parts always hold m*BH + 1 candidates, so the ramp-up and ramp-down
 //   of the rotating accumulators have a static shape and are skipped with
 //   warp-uniform branches: no wasted pixel-compares, no validity tests in the loop.
@@ -61,9 +59,9 @@ namespace me {
 
 namespace {
 
-constexpr int kConsumerWarps = 15;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
-constexpr int kStages = 2;
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxStages = 4;
 constexpr uint32_t kNoKey = 0xffffffffu;
 
 struct TiledParams {
@@ -76,14 +74,13 @@ struct TiledParams {
   int items_per_row;      // ceil(strips_per_row / ns)
   int total_items;        // items_per_row * by_count * npairs
   int wb, wh;             // window box: bytes per row (pitch), rows
-  int copy_bytes;         // wb * wh (multiple of 128)
+  int win_bytes;          // wb * wh rounded up to 128
   int cur_pitch;          // ns * 4 * WORDS bytes
-  int stage_bytes;        // 4 copies + cur tile + best keys, 128-aligned
+  int stage_bytes;        // window + cur tile + best keys, 128-aligned
+  int stages;             // ring depth, 2..kMaxStages
   int parts_target;       // wanted vertical parts per column
-  int partial_w;          // W % strip width != 0: reference bytes right of the frame are masked
   int e;                  // bytes between the 16-aligned TMA origin and the window origin x0-R
-  int cls_u0[4];          // first byte offset u = e + dx of class s = u & 3
-  int cls_n[4];           // number of dx offsets in that class
+  int skew;               // start-up stagger between the warps of one scheduler, in cycles
   Out out;
 };
 
@@ -164,7 +161,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int WORDS, int BH, int NSUB, int FORM>
+template <int WORDS, int BH, int NSUB, int FORM, bool PW>
 __global__ void __launch_bounds__(kThreads, 1)
 tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
                     const __grid_constant__ TiledParams p) {
@@ -172,109 +169,68 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   constexpr int BW = SW / NSUB;       // block width == p.B
   constexpr int WPB = WORDS / NSUB;   // words per block row
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t tma_bar[kStages];    // TMA bytes landed (producer waits)
-  __shared__ __align__(8) uint64_t full_bar[kStages];   // shifted copies built (consumers wait)
-  __shared__ __align__(8) uint64_t empty_bar[kStages];  // all consumer warps left the item
-  __shared__ uint32_t chunk_ctr[kStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];  // TMA bytes of the stage's item have landed
+  __shared__ uint32_t chunk_ctr[kMaxStages];              // next 32-task chunk of the stage's item
+  __shared__ uint32_t left_ctr[kMaxStages];               // warps that are done with the stage's item
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int best_off = 4 * p.copy_bytes + p.cur_pitch * BH;  // byte offset of the key array in a stage
+  const int lane = threadIdx.x & 31;
+  const int cur_off = p.win_bytes;                       // byte offsets inside a stage
+  const int best_off = p.win_bytes + p.cur_pitch * BH;
+  const int grid = (int)gridDim.x;
+  const int nmine = p.total_items > (int)blockIdx.x ? (p.total_items - (int)blockIdx.x + grid - 1) / grid : 0;
+  const int nblk_item = p.ns * NSUB;  // key slots per stage
+
+  // (re)arm a stage with this CTA's k-th item: reset its keys and counters, start the TMA.
+  // Called by one whole warp.
+  auto refill = [&](const int stage, const int k) {
+    uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+    const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
+    for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
+    if (lane == 0) {
+      chunk_ctr[stage] = 0;
+      left_ctr[stage] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // order the generic-proxy accesses to this stage before the async-proxy (TMA) writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
+      mbar_arrive_expect_tx(&full_bar[stage], bytes);
+      // 16-byte aligned origin: e bytes left of the window origin x0 - R
+      tma_load_3d(sb, &map_ref, &full_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
+      tma_load_3d(sb + cur_off, &map_cur, &full_bar[stage], I.strip0 * SW, I.y0, I.pair);
+    }
+    __syncwarp();
+  };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) {
-      mbar_init(&tma_bar[s], 1);
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
-    }
+    for (int s = 0; s < kMaxStages; s++) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x < 32)
+    for (int k = 0; k < p.stages && k < nmine; k++) refill(k, k);
 
-  const int nblk_item = p.ns * NSUB;  // key slots per stage
-
-  if (warp == kConsumerWarps) {
-    // ===================== producer warp =====================
-    const int grid = (int)gridDim.x;
-    const int nmine = p.total_items > (int)blockIdx.x ? (p.total_items - (int)blockIdx.x + grid - 1) / grid : 0;
-    // iteration k: (B) finish the load of item k-1 (build its shifted copies, release it to the
-    // consumers), then (A) recycle the stage of item k-kStages (publish its results) and start
-    // the TMA of item k.  B before A keeps the consumers fed while A waits for them.
-    for (int k = 0; k <= nmine + kStages; k++) {
-      if (k >= 1 && k - 1 < nmine) {
-        const int stage = (k - 1) % kStages;
-        uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
-        mbar_wait(&tma_bar[stage], ((k - 1) / kStages) & 1);
-        const uint32_t *c0 = reinterpret_cast<const uint32_t *>(sb);
-        uint32_t *c1 = reinterpret_cast<uint32_t *>(sb + p.copy_bytes);
-        uint32_t *c2 = reinterpret_cast<uint32_t *>(sb + 2 * (size_t)p.copy_bytes);
-        uint32_t *c3 = reinterpret_cast<uint32_t *>(sb + 3 * (size_t)p.copy_bytes);
-        const int nwords = (p.wb * p.wh) >> 2;
-        // word i of copy s = bytes [4i+s, 4i+s+4) of the window; the word after a row's last one
-        // belongs to the next row, but those bytes lie in the >= 3 byte slack of wb
-#pragma unroll 4
-        for (int i = lane; i < nwords; i += 32) {
-          const uint32_t lo = c0[i], hi = c0[i + 1];
-          c1[i] = __funnelshift_r(lo, hi, 8);
-          c2[i] = __funnelshift_r(lo, hi, 16);
-          c3[i] = __funnelshift_r(lo, hi, 24);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-      }
-      const int stage = k % kStages;
-      uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
-      unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
-      if (k >= kStages && k - kStages < nmine) {
-        // item k - kStages used this stage and is complete: publish its results
-        mbar_wait(&empty_bar[stage], ((k / kStages) - 1) & 1);
-        const Item D = decode_item<BH>(p, (int)blockIdx.x + (k - kStages) * grid);
-        for (int b = lane; b < D.ns * NSUB; b += 32) {
-          const int bx = D.strip0 * NSUB + b;
-          if (bx < p.nbx) {
-            const unsigned long long key = best[b];
-            const uint32_t k32 = (uint32_t)(key >> 32);
-            const uint32_t ssd = k32 >> 8;
-            const size_t oi = (size_t)D.pair * p.nbx * p.nby + (size_t)D.by * p.nbx + bx;
-            if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
-            if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
-            if (p.out.ssd) p.out.ssd[oi] = ssd;
-            const int bw = min(BW, p.W - bx * BW);
-            if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(bw * D.h));  // main.c:27
-          }
-        }
-        __syncwarp();
-      }
-      if (k < nmine) {
-        const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
-        for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
-        if (lane == 0) chunk_ctr[stage] = 0;
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
-          mbar_arrive_expect_tx(&tma_bar[stage], bytes);
-          // 16-byte aligned origin: e bytes left of the window origin x0 - R
-          tma_load_3d(sb, &map_ref, &tma_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
-          tma_load_3d(sb + 4 * (size_t)p.copy_bytes, &map_cur, &tma_bar[stage], I.strip0 * SW, I.y0, I.pair);
-        }
-        __syncwarp();
-      }
+  // Stagger the warps that share a scheduler (warp & 3): they run identical instruction
+  // streams at the same pipe-bound rate, so without a stagger they reach the non-IDP section
+  // at every row boundary together and the FMA pipe idles; an initial offset persists.
+  if (p.skew > 0) {
+    const long long until = clock64() + (long long)(threadIdx.x >> 7) * p.skew;
+    while (clock64() < until) {
     }
-    return;
   }
 
-  // ===================== consumer warps =====================
-  int k = 0;
-  for (int it = blockIdx.x; it < p.total_items; it += gridDim.x, k++) {
-    const int stage = k % kStages;
+  for (int k = 0; k < nmine; k++) {
+    const int stage = k % p.stages;
     uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
-    const Item I = decode_item<BH>(p, it);
-    mbar_wait(&full_bar[stage], (k / kStages) & 1);
+    const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
+    mbar_wait(&full_bar[stage], (k / p.stages) & 1);
 
     const int L = I.m * BH + 1;
-    // tasks are ordered by byte-phase class s = (e + dx) & 3 so that a warp reads one copy
-    const int e1 = I.ns * p.cls_n[0], e2 = e1 + I.ns * p.cls_n[1], e3 = e2 + I.ns * p.cls_n[2];
+    const int ndx = 2 * p.R + 1;
 
     for (;;) {
       int c = 0;
@@ -282,29 +238,23 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c >= I.nchunks) break;
 
-      // ---- decode this lane's task: (part, s, strip, j); dx = 4j + s
+      // ---- decode this lane's task: (part, strip, dx); consecutive lanes = consecutive dx
       int task = c * 32 + lane;
       const bool active = task < I.ntasks;
       task = min(task, I.ntasks - 1);
       const int part = task / I.tpp;
-      int rem = task - part * I.tpp;
-      int s;
-      if (rem < e1) { s = 0; }
-      else if (rem < e2) { s = 1; rem -= e1; }
-      else if (rem < e3) { s = 2; rem -= e2; }
-      else { s = 3; rem -= e3; }
-      const int nj = p.cls_n[s];
-      const int st = rem / nj;
-      const int j = rem - st * nj;
-      const int u = p.cls_u0[s] + 4 * j;  // byte offset from the aligned TMA origin
-      const int dx = u - p.e;             // window-relative horizontal offset, mvx = dx - R
+      const int rem = task - part * I.tpp;
+      const int st = rem / ndx;
+      const int dx = rem - st * ndx;          // window-relative horizontal offset, mvx = dx - R
+      const int u = p.e + st * SW + dx;       // byte offset of the candidate column in a window row
+      const uint32_t shift = 8u * (uint32_t)(u & 3);
       // vertical part: candidates [c0, c0 + L), evenly spread, the last one ends at nc
       const int c0 = I.nparts > 1 ? (int)(((long long)(I.nc - L) * part) / (I.nparts - 1)) : 0;
 
       // ---- current-frame rows of the strip into registers
       uint32_t cur[BH][WORDS];
       {
-        const uint4 *ct = reinterpret_cast<const uint4 *>(sb + 4 * (size_t)p.copy_bytes);
+        const uint4 *ct = reinterpret_cast<const uint4 *>(sb + cur_off);
         const int pitch4 = p.cur_pitch >> 4;
 #pragma unroll
         for (int r = 0; r < BH; r++)
@@ -320,9 +270,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #pragma unroll
       for (int b = 0; b < NSUB; b++) bestk[b] = kNoKey;
 
-      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)s * p.copy_bytes +
-                                                                (size_t)(I.dy_lo + c0) * p.wb) +
-                             st * WORDS + (u >> 2);
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)(I.dy_lo + c0) * p.wb) + (u >> 2);
       const int pitchw = p.wb >> 2;
       const int x_strip = (I.strip0 + st) * SW;
       // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
@@ -331,7 +279,6 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
       uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
       const bool half = I.h != BH;          // bottom block row of height BH/2
-      const bool pw = p.partial_w != 0;
       if (FORM == 1) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
@@ -344,37 +291,52 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #pragma unroll
           for (int r = 0; r < BH; r++) qh[b][r] = 0u;
         }
+        if (PW) {
 #pragma unroll
-        for (int w = 0; w < WORDS; w++) {
-          // bytes of word w that lie inside the frame for the block at x_strip (columns < W)
-          const int left = p.W - (x_strip + 4 * w);
-          msk[w] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+          for (int w = 0; w < WORDS; w++) {
+            // bytes of word w that lie inside the frame for the block at x_strip (columns < W)
+            const int left = p.W - (x_strip + 4 * w);
+            msk[w] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+          }
         }
       }
+
+      // Software pipeline: the raw words of the NEXT row are loaded at the top of a step, so
+      // the LDS latency and the funnel shifts hide behind a whole step of IDP work (the row
+      // after the last one still lies inside the stage; it is loaded but never used).
+      uint32_t raw[WORDS + 1];
+#pragma unroll
+      for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
+      rowp += pitchw;
 
       for (int per = 0; per <= I.m; per++) {
         const bool first = per == 0;
         const bool last = per == I.m;
 #pragma unroll
         for (int s_ = 0; s_ < BH; s_++) {
+          // byte-align this row to the candidate column, then fetch the next row
           uint32_t ref[WORDS];
 #pragma unroll
-          for (int w = 0; w < WORDS; w++) ref[w] = rowp[w];
+          for (int w = 0; w < WORDS; w++) ref[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
+#pragma unroll
+          for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
           rowp += pitchw;
 
           if (FORM == 1) {
-            // energy of this reference row over each block's columns, then slide the window:
+            // energy of this reference row over each block's columns (bytes right of the frame
+            // masked out when PW), as two independent IDP chains, then slide the window:
             // full height: + q(t) - q(t-BH);  half height: + q(t-BH/2) - q(t-BH)
 #pragma unroll
             for (int b = 0; b < NSUB; b++) {
-              uint32_t qt = 0;
-              if (pw) {
+              uint32_t q0 = 0, q1 = 0;
 #pragma unroll
-                for (int w = 0; w < WPB; w++) qt = __dp4a(ref[b * WPB + w] & msk[b * WPB + w], ref[b * WPB + w], qt);
-              } else {
-#pragma unroll
-                for (int w = 0; w < WPB; w++) qt = __dp4a(ref[b * WPB + w], ref[b * WPB + w], qt);
+              for (int w = 0; w < WPB; w++) {
+                const uint32_t x = ref[b * WPB + w];
+                const uint32_t xm = PW ? (x & msk[b * WPB + w]) : x;
+                if (w & 1) q1 = __dp4a(xm, x, q1);
+                else q0 = __dp4a(xm, x, q0);
               }
+              const uint32_t qt = q0 + q1;
               const uint32_t add = half ? qh[b][(s_ + BH / 2) % BH] : qt;
               srun[b] = srun[b] + add - qh[b][s_];
               qh[b][s_] = qt;
@@ -405,15 +367,26 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
               }
             }
           };
+#ifdef ME_EXPERIMENT_NOSKIP
+          // experiment only (wrong results): no ramp skipping, hence no branches in the step
+#pragma unroll
+          for (int r = 0; r < BH; r++) group(r);
+#else
+          // ramp-down (last period): candidates that started in this period do not exist -> only
+          // r >= s_; ramp-up (first period): candidates from the previous period do not exist ->
+          // only r <= s_.  The diagonal group r == s_ always runs; it is emitted inside the second
+          // region (and alone in its else branch) so that it is scheduled among independent work.
           if (!last) {
 #pragma unroll
             for (int r = 0; r < s_; r++) group(r);
           }
-          group(s_);
           if (!first) {
 #pragma unroll
-            for (int r = s_ + 1; r < BH; r++) group(r);
+            for (int r = s_; r < BH; r++) group(r);
+          } else {
+            group(s_);
           }
+#endif
         }
         dy_fin += BH;
       }
@@ -434,8 +407,33 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           atomicMin(&best[st * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
       }
     }
+    // ---- leave the item; the last warp out publishes it and re-arms the stage
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    int prev = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      prev = (int)atomicAdd(&left_ctr[stage], 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == kWarps - 1) {
+      __threadfence_block();
+      for (int b = lane; b < I.ns * NSUB; b += 32) {
+        const int bx = I.strip0 * NSUB + b;
+        if (bx < p.nbx) {
+          const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[b]);
+          const uint32_t k32 = (uint32_t)(key >> 32);
+          const uint32_t ssd = k32 >> 8;
+          const size_t oi = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
+          if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
+          if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
+          if (p.out.ssd) p.out.ssd[oi] = ssd;
+          const int bw = min(BW, p.W - bx * BW);
+          if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(bw * I.h));  // main.c:27
+        }
+      }
+      __syncwarp();
+      if (k + p.stages < nmine) refill(stage, k + p.stages);
+    }
   }
 }
 
@@ -511,8 +509,8 @@ void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
 
 namespace {
 
-template <int WORDS, int BH, int NSUB, int FORM>
-cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
+template <int WORDS, int BH, int NSUB, int FORM, bool PW>
+cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          int by_begin, int by_count, cudaStream_t s, const char **err) {
   constexpr int SW = 4 * WORDS;
   TiledParams p;
@@ -526,18 +524,21 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
   const int static_smem = 256;
   const int ebytes = (16 - (g.R % 16)) % 16;  // SW is a multiple of 16, so every item has the same phase
   // Choose strips per item (ns) and vertical parts per column with a small cost model:
-  // a CTA's time ~ (items it owns) x (chunks per item) x (instructions per task) / consumer warps.
+  // a CTA's time ~ (items it owns) x (chunks per item) x (instructions per task) / warps.
   // ns is bounded by the TMA box (<= 256 B per row) and by two stages of shared memory.
   const long long rows_total = (long long)by_count * npairs;
   const int nc = 2 * g.R + 1;
   double best_cost = 1e300;
   int best_ns = 0, best_parts = 1;
+  auto stage_size = [&](int ns) {
+    const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
+    const int win = ((wb * p.wh) + 127) & ~127;
+    return (win + ns * SW * BH + ns * NSUB * 8 + 127) & ~127;
+  };
   for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
-    const int wb = (ebytes + ns * SW + 2 * g.R + 3 + 15) & ~15;
+    const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
     if (wb > 256 || ns * SW > 256) break;
-    const int copy = ((wb * p.wh) + 127) & ~127;
-    const int stage = (4 * copy + ns * SW * BH + ns * NSUB * 8 + 127) & ~127;
-    if (kStages * stage + static_smem > plan->max_smem) break;
+    if (2 * stage_size(ns) + static_smem > plan->max_smem) break;
     if (plan->ns_override > 0 && ns != plan->ns_override) continue;
     const long long items = rows_total * ((p.strips_per_row + ns - 1) / ns);
     const long long per_cta = (items + plan->sms - 1) / plan->sms;
@@ -549,10 +550,12 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
       const int L = m * BH + 1;
       const int nparts = (nc + L - 1) / L;
       const long long chunks = ((long long)ns * nc * nparts + 31) / 32;
-      // per task: L candidates x BH rows x WORDS x 2 int ops, plus per streamed row WORDS LDS + ~4
-      const double task = (double)L * BH * WORDS * 2.0 + (double)(L + BH - 1) * (WORDS + 4.0) + 150.0;
+      // per task: L candidates x BH rows x WORDS cross-term ops (x2 for FORM 0), plus per streamed
+      // row the loads, shifts and (FORM 1) the row-energy ops
+      const double per_row = FORM == 1 ? (2.0 * WORDS + 8.0) : (2.0 * WORDS + 6.0);
+      const double task = (double)L * BH * WORDS * (FORM == 1 ? 1.0 : 2.0) + (double)(L + BH - 1) * per_row + 250.0;
       // warps flow from one item into the next, so chunks only quantise over the CTA's whole run
-      const double cost = (double)((per_cta * chunks + kConsumerWarps - 1) / kConsumerWarps) * task;
+      const double cost = (double)((per_cta * chunks + kWarps - 1) / kWarps) * task + 0.02 * per_cta * 2000.0;
       if (cost < best_cost * 0.999) { best_cost = cost; best_ns = ns; best_parts = parts; }
     }
   }
@@ -562,18 +565,18 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
   p.parts_target = best_parts;
   p.items_per_row = (p.strips_per_row + ns - 1) / ns;
   p.total_items = (int)(p.items_per_row * rows_total);
-  p.wb = (ebytes + ns * SW + 2 * g.R + 3 + 15) & ~15;
+  p.wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
   p.e = ebytes;
-  for (int c = 0; c < 4; c++) {
-    const int u0 = ebytes + (((c - ebytes) % 4) + 4) % 4;
-    p.cls_u0[c] = u0;
-    p.cls_n[c] = u0 <= ebytes + 2 * g.R ? (ebytes + 2 * g.R - u0) / 4 + 1 : 0;
-  }
-  p.copy_bytes = ((p.wb * p.wh) + 127) & ~127;
+  p.win_bytes = ((p.wb * p.wh) + 127) & ~127;
   p.cur_pitch = ns * SW;
-  p.stage_bytes = (4 * p.copy_bytes + p.cur_pitch * BH + ns * NSUB * 8 + 127) & ~127;
-  p.partial_w = (g.W % SW) != 0;
+  p.stage_bytes = stage_size(ns);
+  p.stages = (plan->max_smem - static_smem) / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.out = o;
+  {
+    const char *sk = getenv("ME_B200_SKEW");
+    p.skew = sk ? atoi(sk) : 0;
+  }
 
   EncodeTiledFn enc = get_encode();
   if (!enc) { *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
@@ -595,8 +598,8 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
     *err = msg;
     return cudaErrorInvalidValue;
   }
-  const int smem = kStages * p.stage_bytes;
-  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM>;
+  const int smem = p.stages * p.stage_bytes;
+  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; return e; }
   const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
@@ -604,6 +607,16 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
   return e;
+}
+
+template <int WORDS, int BH, int NSUB, int FORM>
+cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
+                         int by_begin, int by_count, cudaStream_t s, const char **err) {
+  // PW: the frame width is not a multiple of the strip width, so the last strip holds a
+  // partial-width block whose out-of-block reference bytes must be masked (FORM 1 only)
+  if (FORM == 1 && (g.W % (4 * WORDS)) != 0)
+    return launch_shape_pw<WORDS, BH, NSUB, FORM, true>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+  return launch_shape_pw<WORDS, BH, NSUB, FORM, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
 }
 
 }  // namespace

@@ -27,7 +27,7 @@ ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED = 0, 1, 2
 ME_B200_MAX_SLOTS = 4
 
 PEAK_NAMES = ["IDP4A", "VABSDIFF4", "SSD_PAIR", "IADD3", "LOP3", "IMAD", "VIMNMX",
-              "SSD_PAIR_LDS", "IDP4A_IADD3"]
+              "SSD_PAIR_LDS", "IDP4A_IADD3", "LOOP_REPLICA"]
 
 
 class MeError(RuntimeError):
