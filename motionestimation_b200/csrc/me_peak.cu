@@ -130,7 +130,8 @@ double run_replica(int iters, double *mhz) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0.0;
-  const int ctas = sms, threads = 512;
+  const char *et = getenv("ME_PEAK_THREADS");
+  const int ctas = sms, threads = et ? atoi(et) : 512;
   uint32_t *out = nullptr;
   unsigned long long *clk = nullptr;
   if (cudaMalloc(&out, (size_t)ctas * threads * 4) != cudaSuccess) return 0.0;

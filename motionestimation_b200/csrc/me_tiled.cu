@@ -59,7 +59,10 @@ namespace me {
 
 namespace {
 
-constexpr int kWarps = 16;
+#ifndef ME_WARPS
+#define ME_WARPS 16
+#endif
+constexpr int kWarps = ME_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 4;
 constexpr uint32_t kNoKey = 0xffffffffu;
@@ -309,9 +312,13 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
       rowp += pitchw;
 
-      for (int per = 0; per <= I.m; per++) {
+      // the period count is the same for the whole warp; routing it through a warp reduction puts
+      // it in a uniform register, so the ramp branches below compile to uniform branches without
+      // divergence bookkeeping (BSSY/BSYNC)
+      const int m_uni = __reduce_max_sync(0xffffffffu, I.m);
+      for (int per = 0; per <= m_uni; per++) {
         const bool first = per == 0;
-        const bool last = per == I.m;
+        const bool last = per == m_uni;
 #pragma unroll
         for (int s_ = 0; s_ < BH; s_++) {
           // byte-align this row to the candidate column, then fetch the next row
