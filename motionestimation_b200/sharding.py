@@ -1,0 +1,127 @@
+"""Multi-GPU partitioning of the search.
+
+The reference has no multi-device code at all (its only parallelism is one
+thread-pool job per block, ``src/cpu/main.c:144-158``); blocks -- and therefore
+frame pairs -- are independent, which gives two shardings, one process per GPU:
+
+* **by frame pair** (the batched workloads): rank r owns a contiguous slice of the
+  batch and writes its own slice of the motion field.  No data-path collective.
+* **by block-row band** (one very large frame): rank r searches block rows
+  ``[band_rows(...)]`` of every pair with ``me_b200_search_device_band`` -- the kernel
+  reads the reference rows of the band +- R straight from the rank's copy of the
+  frame, so there is no halo exchange -- and ONE collective at the end gathers the
+  per-band slices of the field (``all_gather`` over NCCL on GPUs; gloo in CPU tests).
+
+torch.distributed is plumbing here: rendezvous and the gather.  The search is
+always the CUDA library.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+
+def pair_slice(npairs: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of a batch of frame pairs owned by `rank`
+    (sizes differ by at most one, earlier ranks take the remainder)."""
+    if world < 1 or not 0 <= rank < world or npairs < 0:
+        raise ValueError("bad partition arguments")
+    base, rem = divmod(npairs, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def band_rows(nby: int, world: int, rank: int, weights: Optional[Sequence[float]] = None) -> Tuple[int, int]:
+    """Block rows [begin, end) of rank `rank` when one frame is split into bands.
+    With `weights` (one cost per block row, e.g. from :func:`row_costs`) the cut
+    points balance cost instead of row count (border rows are cheaper: their
+    windows are clamped, main.c:73-76)."""
+    if world < 1 or not 0 <= rank < world or nby < 0:
+        raise ValueError("bad partition arguments")
+    if weights is None:
+        return pair_slice(nby, world, rank)
+    if len(weights) != nby:
+        raise ValueError("one weight per block row expected")
+    total = float(sum(weights))
+    cuts = [0]
+    acc, row = 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while row < nby and acc + weights[row] / 2.0 <= target:
+            acc += weights[row]
+            row += 1
+        cuts.append(row)
+    cuts.append(nby)
+    for i in range(1, len(cuts)):           # monotone, never empty unless nby < world
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
+def row_costs(width: int, height: int, blk_dim: int, extra_span: int) -> List[int]:
+    """Pixel-compares of each block row: the separable count
+    (sum_x w*ncx) * (h*ncy) with clamped candidate ranges."""
+    def axis(n):
+        out = []
+        for p in range(0, n, blk_dim):
+            e = min(blk_dim, n - p)
+            lo = max(0, p - extra_span)
+            hi = min(n - 1, p + e - 1 + extra_span)
+            out.append(e * (hi - e + 1 - lo + 1))
+        return out
+    sx = sum(axis(width))
+    return [sx * c for c in axis(height)]
+
+
+def gather_bands(local: "torch.Tensor", rows: Tuple[int, int], nby: int, nbx: int, group=None):
+    """All-gather the per-band slices of a field.
+
+    `local` is this rank's (npairs, (rows[1]-rows[0]) * nbx) tensor (any dtype,
+    CUDA for NCCL, CPU for gloo).  Returns the full (npairs, nby * nbx) field on
+    every rank.  Bands may have different heights, so slices are padded to the
+    tallest band for the collective and trimmed afterwards.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    npairs = local.shape[0]
+    mine = torch.tensor([rows[0], rows[1]], dtype=torch.int64, device=local.device)
+    all_rows = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(all_rows, mine, group=group)
+    spans = [(int(t[0]), int(t[1])) for t in all_rows]
+    tallest = max(e - b for b, e in spans)
+    padded = torch.zeros((npairs, tallest * nbx), dtype=local.dtype, device=local.device)
+    padded[:, : local.shape[1]] = local
+    parts = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    full = torch.zeros((npairs, nby * nbx), dtype=local.dtype, device=local.device)
+    covered = 0
+    for (b, e), part in zip(spans, parts):
+        full[:, b * nbx: e * nbx] = part[:, : (e - b) * nbx]
+        covered += e - b
+    if covered != nby:
+        raise RuntimeError("bands do not tile the frame: %r" % (spans,))
+    return full
+
+
+def search_banded(est, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, group=None, stream: int = 0,
+                  balance: bool = True):
+    """One frame (or batch) split by block-row bands over the ranks of `group`.
+    Every rank holds the full frames on its GPU, searches its band and gathers the
+    field.  Returns dict(mvx, mvy, ssd, score) of full (npairs, num_blocks) CUDA tensors."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    weights = row_costs(est.width, est.height, est.blk_dim, est.extra_span) if balance else None
+    b0, b1 = band_rows(est.blocks_y, world, rank, weights)
+    nb = est.num_blocks
+    dev = d_cur.device
+    out = {k: torch.zeros((npairs, nb), dtype=dt, device=dev)
+           for k, dt in (("mvx", torch.int32), ("mvy", torch.int32), ("ssd", torch.int32), ("score", torch.float32))}
+    est.search_device(d_cur, d_ref, pitch, pair_stride, npairs, out["mvx"], out["mvy"], out["ssd"], out["score"],
+                      stream, b0, b1)
+    nbx = est.blocks_x
+    res = {}
+    for k, t in out.items():
+        res[k] = gather_bands(t[:, b0 * nbx: b1 * nbx].contiguous(), (b0, b1), est.blocks_y, nbx, group)
+    return res
