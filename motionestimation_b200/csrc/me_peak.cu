@@ -84,8 +84,15 @@ __global__ void __launch_bounds__(512) peak_kernel(uint32_t *out, int iters, uin
 // registers, 16 rotating accumulators, 4 "reference" registers refreshed by one LOP3 each per
 // row step, 64 IDP.4A per step in the same register pattern.  Measures what the FMA pipe
 // sustains for that operand pattern at the search kernel's occupancy.
+// VARIANT bit 0: two warp-uniform branches per row step (as the ramp skipping of the real loop);
+//         bit 1: 5 LDS.32 + 4 funnel shifts per row step (the real loop's row fetch);
+//         bit 2: start the warps of one scheduler at different loop phases.
+template <int VARIANT>
 __global__ void __launch_bounds__(512, 1) replica_kernel(uint32_t *out, int iters, uint32_t seed,
-                                                         unsigned long long *clk) {
+                                                         unsigned long long *clk, int flags) {
+  __shared__ uint32_t rows[64 * 64];
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) rows[i] = seed * (i + 1);
+  __syncthreads();
   uint32_t cur[16][4], acc[16], ref[4];
 #pragma unroll
   for (int r = 0; r < 16; r++)
@@ -100,20 +107,49 @@ __global__ void __launch_bounds__(512, 1) replica_kernel(uint32_t *out, int iter
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     t0 = clock64();
   }
+  if (VARIANT & 4) {
+    const long long until = clock64() + (long long)(threadIdx.x >> 7) * 137;
+    while (clock64() < until) {
+    }
+  }
   uint32_t best = 0xffffffffu;
+  const uint32_t *rowp = rows + (threadIdx.x & 31);
+  const uint32_t shift = 8u * (threadIdx.x & 3);
+  const bool fa = (flags & 1) != 0, fb = (flags & 2) != 0;   // both true at run time
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int s_ = 0; s_ < 16; s_++) {
+      if (VARIANT & 2) {
+        uint32_t raw[5];
 #pragma unroll
-      for (int w = 0; w < 4; w++) ref[w] = (ref[w] ^ best) + 0x01010101u * (w + 1);
+        for (int w = 0; w < 5; w++) raw[w] = rowp[s_ * 64 + w];
 #pragma unroll
-      for (int r = 0; r < 16; r++) {
+        for (int w = 0; w < 4; w++) ref[w] = __funnelshift_r(raw[w], raw[w + 1], shift) ^ best;
+      } else {
+#pragma unroll
+        for (int w = 0; w < 4; w++) ref[w] = (ref[w] ^ best) + 0x01010101u * (w + 1);
+      }
+      auto group = [&](const int r) {
         const int slot = (s_ - r + 16) % 16;
         uint32_t a = r == 0 ? 0u : acc[slot];
 #pragma unroll
         for (int w = 0; w < 4; w++) a = __dp4a(cur[r][w], ref[w], a);
         acc[slot] = a;
         if (r == 15) best = min(best, (a << 8) + (uint32_t)s_);
+      };
+      if (VARIANT & 1) {
+        if (fa) {
+#pragma unroll
+          for (int r = 0; r < s_; r++) group(r);
+        }
+        if (fb) {
+#pragma unroll
+          for (int r = s_ + 1; r < 16; r++) group(r);
+        }
+        group(s_);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; r++) group(r);
       }
     }
   }
@@ -126,6 +162,7 @@ __global__ void __launch_bounds__(512, 1) replica_kernel(uint32_t *out, int iter
   if (best == 0x12345679u) out[blockIdx.x * blockDim.x + threadIdx.x] = best;
 }
 
+template <int VARIANT>
 double run_replica(int iters, double *mhz) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -139,9 +176,9 @@ double run_replica(int iters, double *mhz) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  replica_kernel<<<ctas, threads>>>(out, iters / 8 + 1, 12345u, clk);
+  replica_kernel<VARIANT><<<ctas, threads>>>(out, iters / 8 + 1, 12345u, clk, 3);
   cudaEventRecord(e0);
-  replica_kernel<<<ctas, threads>>>(out, iters, 12345u, clk);
+  replica_kernel<VARIANT><<<ctas, threads>>>(out, iters, 12345u, clk, 3);
   cudaEventRecord(e1);
   double rate = 0.0;
   if (cudaEventSynchronize(e1) == cudaSuccess) {
@@ -216,7 +253,17 @@ extern "C" double me_b200_int_peak(int device, int which, int iters, double *sm_
     case ME_PEAK_VIMNMX: return run_peak<ME_PEAK_VIMNMX>(iters, sm_clock_mhz);
     case ME_PEAK_SSD_PAIR_LDS: return run_peak<ME_PEAK_SSD_PAIR_LDS>(iters, sm_clock_mhz);
     case ME_PEAK_IDP4A_IADD3: return run_peak<ME_PEAK_IDP4A_IADD3>(iters, sm_clock_mhz);
-    case ME_PEAK_LOOP_REPLICA: return run_replica(iters / 16 + 1, sm_clock_mhz);
+    case ME_PEAK_LOOP_REPLICA: {
+      const char *v = getenv("ME_PEAK_REPLICA_VARIANT");
+      switch (v ? atoi(v) : 0) {
+        case 1: return run_replica<1>(iters / 16 + 1, sm_clock_mhz);
+        case 2: return run_replica<2>(iters / 16 + 1, sm_clock_mhz);
+        case 3: return run_replica<3>(iters / 16 + 1, sm_clock_mhz);
+        case 7: return run_replica<7>(iters / 16 + 1, sm_clock_mhz);
+        case 4: return run_replica<4>(iters / 16 + 1, sm_clock_mhz);
+        default: return run_replica<0>(iters / 16 + 1, sm_clock_mhz);
+      }
+    }
     default: return 0.0;
   }
 }

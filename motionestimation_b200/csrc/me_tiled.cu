@@ -65,6 +65,8 @@ namespace {
 constexpr int kWarps = ME_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 4;
+constexpr int kWinPitch = 256;  // window row pitch in shared memory = TMA box width (the maximum);
+                                // a compile-time pitch turns every row offset into an LDS immediate
 constexpr uint32_t kNoKey = 0xffffffffu;
 
 struct TiledParams {
@@ -273,8 +275,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #pragma unroll
       for (int b = 0; b < NSUB; b++) bestk[b] = kNoKey;
 
-      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)(I.dy_lo + c0) * p.wb) + (u >> 2);
-      const int pitchw = p.wb >> 2;
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)(I.dy_lo + c0) * kWinPitch) + (u >> 2);
+      constexpr int pitchw = kWinPitch >> 2;
       const int x_strip = (I.strip0 + st) * SW;
       // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
       int dy_fin = I.dy_lo + c0 - (BH - 1);
@@ -323,12 +325,18 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         for (int s_ = 0; s_ < BH; s_++) {
           // byte-align this row to the candidate column, then fetch the next row
           uint32_t ref[WORDS];
+#ifdef ME_EXPERIMENT_NOLOAD
+#pragma unroll
+          for (int w = 0; w < WORDS; w++) ref[w] = raw[w] + (uint32_t)s_;
+#else
 #pragma unroll
           for (int w = 0; w < WORDS; w++) ref[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
 #pragma unroll
           for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
           rowp += pitchw;
+#endif
 
+#ifndef ME_EXPERIMENT_NOQ
           if (FORM == 1) {
             // energy of this reference row over each block's columns (bytes right of the frame
             // masked out when PW), as two independent IDP chains, then slide the window:
@@ -349,6 +357,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
               qh[b][s_] = qt;
             }
           }
+#endif
 
           // one (current row r) x (this reference row) group: slot (s_ - r) mod BH
           auto group = [&](const int r) {
@@ -381,18 +390,17 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #else
           // ramp-down (last period): candidates that started in this period do not exist -> only
           // r >= s_; ramp-up (first period): candidates from the previous period do not exist ->
-          // only r <= s_.  The diagonal group r == s_ always runs; it is emitted inside the second
-          // region (and alone in its else branch) so that it is scheduled among independent work.
+          // only r <= s_.  The diagonal group r == s_ always runs; placed last it shares a basic
+          // block with the next step's shifts, loads and row energy, i.e. independent work.
           if (!last) {
 #pragma unroll
             for (int r = 0; r < s_; r++) group(r);
           }
           if (!first) {
 #pragma unroll
-            for (int r = s_; r < BH; r++) group(r);
-          } else {
-            group(s_);
+            for (int r = s_ + 1; r < BH; r++) group(r);
           }
+          group(s_);
 #endif
         }
         dy_fin += BH;
@@ -538,7 +546,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   double best_cost = 1e300;
   int best_ns = 0, best_parts = 1;
   auto stage_size = [&](int ns) {
-    const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
+    const int wb = kWinPitch;
     const int win = ((wb * p.wh) + 127) & ~127;
     return (win + ns * SW * BH + ns * NSUB * 8 + 127) & ~127;
   };
@@ -572,7 +580,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.parts_target = best_parts;
   p.items_per_row = (p.strips_per_row + ns - 1) / ns;
   p.total_items = (int)(p.items_per_row * rows_total);
-  p.wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
+  p.wb = kWinPitch;
   p.e = ebytes;
   p.win_bytes = ((p.wb * p.wh) + 127) & ~127;
   p.cur_pitch = ns * SW;
