@@ -31,6 +31,12 @@
 //                instructions of FORM 0 (the unrolled loop fits the instruction cache),
 //                FMA-pipe bound, and zero-padded current rows/columns make partial edge
 //                blocks free (their reference pixels are masked out of sum ref^2).
+//         FORM 2  as FORM 1, but sum ref^2 of every candidate position comes from a table that a
+//                small pre-pass kernel (box_energy_kernel) builds per reference frame; the tile of
+//                the table that belongs to an item rides in the stage next to the window (third
+//                TMA load), so a finished candidate costs one LDS instead of 4 IDP.4A per row
+//                step.  Used when the geometry has no partial-width blocks and the bigger stage
+//                still fits twice; otherwise FORM 1.
 //         FORM 0  |cur-ref| then square: VABSDIFF4.U8 (ALU pipe) + IDP.4A.U8.U8 (FMA pipe)
 //                per 4 pixels; kept for A/B measurements (env ME_B200_FORM=0), full blocks only.
 //     * a candidate that has seen its BH rows is folded into the thread's running
@@ -86,6 +92,10 @@ struct TiledParams {
   int parts_target;       // wanted vertical parts per column
   int e;                  // bytes between the 16-aligned TMA origin and the window origin x0-R
   int skew;               // start-up stagger between the warps of one scheduler, in cycles
+  int s_pitch, s_rows;    // FORM 2: energy tile, elements per row / rows (2R+1)
+  int s_bytes;            // FORM 2: tile bytes rounded up to 128
+  int e_s;                // FORM 2: elements between the 4-aligned TMA origin and x0-R
+  int s_y0;               // FORM 2: frame row of the table's first row
   Out out;
 };
 
@@ -169,6 +179,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
 template <int WORDS, int BH, int NSUB, int FORM, bool PW>
 __global__ void __launch_bounds__(kThreads, 1)
 tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
+                    const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_sh,
                     const __grid_constant__ TiledParams p) {
   constexpr int SW = 4 * WORDS;       // strip width in pixels
   constexpr int BW = SW / NSUB;       // block width == p.B
@@ -180,7 +191,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 
   const int lane = threadIdx.x & 31;
   const int cur_off = p.win_bytes;                       // byte offsets inside a stage
-  const int best_off = p.win_bytes + p.cur_pitch * BH;
+  const int s_off = p.win_bytes + p.cur_pitch * BH;      // FORM 2: energy tile
+  const int best_off = s_off + (FORM == 2 ? p.s_bytes : 0);
   const int grid = (int)gridDim.x;
   const int nmine = p.total_items > (int)blockIdx.x ? (p.total_items - (int)blockIdx.x + grid - 1) / grid : 0;
   const int nblk_item = p.ns * NSUB;  // key slots per stage
@@ -200,11 +212,20 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     if (lane == 0) {
       // order the generic-proxy accesses to this stage before the async-proxy (TMA) writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
+      uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
+      if (FORM == 2) bytes += (uint32_t)(p.s_pitch * p.s_rows * 4);
       mbar_arrive_expect_tx(&full_bar[stage], bytes);
       // 16-byte aligned origin: e bytes left of the window origin x0 - R
       tma_load_3d(sb, &map_ref, &full_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
       tma_load_3d(sb + cur_off, &map_cur, &full_bar[stage], I.strip0 * SW, I.y0, I.pair);
+      if (FORM == 2) {
+        // energy tile: rows = window-relative dy 0..2R.  The half-height bottom row has its own
+        // table whose row 0 is dy = 0 of that block row.
+        if (I.h == BH)
+          tma_load_3d(sb + s_off, &map_s, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, I.y0 - p.R - p.s_y0, I.pair);
+        else
+          tma_load_3d(sb + s_off, &map_sh, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, 0, I.pair);
+      }
     }
     __syncwarp();
   };
@@ -284,7 +305,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
       uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
       const bool half = I.h != BH;          // bottom block row of height BH/2
-      if (FORM == 1) {
+      if (FORM >= 1) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
           uint32_t a = 0;
@@ -296,7 +317,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #pragma unroll
           for (int r = 0; r < BH; r++) qh[b][r] = 0u;
         }
-        if (PW) {
+        if (PW && FORM == 1) {
 #pragma unroll
           for (int w = 0; w < WORDS; w++) {
             // bytes of word w that lie inside the frame for the block at x_strip (columns < W)
@@ -318,6 +339,10 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // it in a uniform register, so the ramp branches below compile to uniform branches without
       // divergence bookkeeping (BSSY/BSYNC)
       const int m_uni = __reduce_max_sync(0xffffffffu, I.m);
+      // FORM 2: energy-table entry of the candidate that finishes at step 0 of the current period
+      // (only dereferenced for candidates that exist)
+      const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * p.s_pitch +
+                            p.e_s + st * SW + dx;
       for (int per = 0; per <= m_uni; per++) {
         const bool first = per == 0;
         const bool last = per == m_uni;
@@ -367,7 +392,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
               uint32_t a = (r == 0) ? 0u : acc[b][slot];
 #pragma unroll
               for (int w = 0; w < WPB; w++) {
-                if (FORM == 1) {
+                if (FORM >= 1) {
                   a = __dp4a(cur[r][b * WPB + w], ref[b * WPB + w], a);
                 } else {
                   const uint32_t d = __vabsdiffu4(cur[r][b * WPB + w], ref[b * WPB + w]);
@@ -377,7 +402,9 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
               acc[b][slot] = a;
               if (r == BH - 1) {
                 // candidate complete: fold (ssd << 8 | dy) into the running minimum
-                const uint32_t ssd = FORM == 1 ? srun[b] - 2u * a : a;
+                uint32_t ssd = a;
+                if (FORM == 1) ssd = srun[b] - 2u * a;
+                if (FORM == 2) ssd = srun[b] + spf[s_ * p.s_pitch + b * BW] - 2u * a;
                 const uint32_t key = (ssd << 8) + (uint32_t)(dy_fin + s_);
                 bestk[b] = min(bestk[b], key);
               }
@@ -404,6 +431,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #endif
         }
         dy_fin += BH;
+        if (FORM == 2) spf += BH * p.s_pitch;
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
@@ -452,6 +480,78 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------- FORM 2 pre-pass
+// box_energy_kernel: E(x, y) = sum of ref^2 over the bw x bh box whose top-left pixel is (x, y),
+// for table rows y = y_lo .. y_lo + nrows - 1 and all x (boxes that leave the frame read zeros and
+// are never used: such candidates do not exist).  One CTA = 128 x 40 table entries:
+//   1. the pixels (+ halo) are staged in shared memory with 32-bit loads,
+//   2. every aligned word gets its sum of 4 squares (one IDP.4A),
+//   3. horizontal box sums: the 4-aligned position adds bw/4 word sums, the three positions after
+//      it slide one pixel at a time (- leaving^2 + entering^2),
+//   4. vertical box sums: one thread per column slides down the tile (+ entering row - leaving row)
+//      and writes coalesced rows.
+// Near HBM-bound (1 B read, 4 B written per entry); runs once per reference frame and launch.
+constexpr int kEx = 128, kEy = 40, kEMax = 16;
+constexpr int kEWords = (kEx + kEMax) / 4;  // aligned words per staged row
+
+__global__ void __launch_bounds__(256)
+box_energy_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_stride, int W, int H, int bw, int bh,
+                  int y_lo, int nrows, uint32_t *__restrict__ out, int out_pitch, size_t out_pair_stride) {
+  __shared__ uint32_t px[kEy + kEMax - 1][kEWords];   // pixels, 4 per word
+  __shared__ uint32_t ws[kEy + kEMax - 1][kEWords];   // sum of squares of each aligned word
+  __shared__ uint32_t hs[kEy + kEMax - 1][kEx];       // horizontal box sums
+  const int x0 = blockIdx.x * kEx, r0 = blockIdx.y * kEy;  // r0: table row of this tile
+  const uint8_t *src = ref + (size_t)blockIdx.z * pair_stride;
+  const int rows_out = min(kEy, nrows - r0);
+  const int rows_in = rows_out + bh - 1;
+  const bool aligned = ((pitch & 3) == 0) && ((((uintptr_t)src) & 3) == 0);
+  for (int i = threadIdx.x; i < rows_in * kEWords; i += 256) {
+    const int r = i / kEWords, k = i - r * kEWords;
+    const int y = y_lo + r0 + r, x = x0 + 4 * k;
+    uint32_t w = 0;
+    if (y >= 0 && y < H && x < W) {
+      const uint8_t *q = src + (size_t)y * pitch + x;
+      if (aligned && x + 4 <= W) {
+        w = *reinterpret_cast<const uint32_t *>(q);
+      } else {
+        for (int b = 0; b < 4; b++)
+          if (x + b < W) w |= (uint32_t)q[b] << (8 * b);
+      }
+    }
+    px[r][k] = w;
+    ws[r][k] = __dp4a(w, w, 0u);
+  }
+  __syncthreads();
+  const int wpb = bw >> 2;  // aligned words per box (bw is 8 or 16)
+  for (int i = threadIdx.x; i < rows_in * (kEx / 4); i += 256) {
+    const int r = i / (kEx / 4), k = i - r * (kEx / 4);
+    uint32_t a = 0;
+    for (int j = 0; j < wpb; j++) a += ws[r][k + j];
+    const uint32_t lo = px[r][k], hi = px[r][k + wpb];  // pixels leaving / entering as the box slides
+    uint32_t o[4];
+    o[0] = a;
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const uint32_t l = (lo >> (8 * b)) & 0xffu, e = (hi >> (8 * b)) & 0xffu;
+      a = a - l * l + e * e;
+      o[b + 1] = a;
+    }
+    *reinterpret_cast<uint4 *>(&hs[r][4 * k]) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  const int c = threadIdx.x;  // one column per thread
+  if (c < kEx && x0 + c < out_pitch) {
+    uint32_t *dst = out + (size_t)blockIdx.z * out_pair_stride + (size_t)r0 * out_pitch + x0 + c;
+    uint32_t a = 0;
+    for (int k = 0; k < bh; k++) a += hs[k][c];
+    dst[0] = a;
+    for (int r = 1; r < rows_out; r++) {
+      a = a + hs[r + bh - 1][c] - hs[r - 1][c];
+      dst[(size_t)r * out_pitch] = a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -480,12 +580,15 @@ struct TiledPlan {
   int max_smem = 0;
   int parts_target = 0;
   int ns_override = 0;
-  int form = 1;  // 1: dot-product expansion (default), 0: |a-b|^2 (env ME_B200_FORM=0)
+  int form = 2;  // 2: energy table when possible, else 1 (default); 1: on-the-fly energies;
+                 // 0: |a-b|^2 -- env ME_B200_FORM selects 0/1 for A/B measurements
 };
 
 static int env_form() {
   const char *f = getenv("ME_B200_FORM");
-  return (f && f[0] == '0') ? 0 : 1;
+  if (f && f[0] == '0') return 0;
+  if (f && f[0] == '1') return 1;
+  return 2;
 }
 
 bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
@@ -504,6 +607,7 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
   if (!shape_ok(g.B)) return cudaErrorNotSupported;
   TiledPlan *pl = new TiledPlan();
   pl->form = env_form();
+
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, dev);
@@ -511,6 +615,15 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
   if (e != cudaSuccess) {
     delete pl;
     return e;
+  }
+  {
+    // the energy tables live in stream-ordered scratch: keep the pool's memory between launches
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
   }
   const char *pt = getenv("ME_B200_PARTS");
   const char *ns = getenv("ME_B200_NS");
@@ -536,7 +649,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.npairs = npairs;
   p.strips_per_row = (g.nbx + NSUB - 1) / NSUB;
   p.wh = 2 * g.R + BH;
-  const int static_smem = 256;
+  const int static_smem = 2048;  // static shared memory (barriers, counters) + alignment slack
   const int ebytes = (16 - (g.R % 16)) % 16;  // SW is a multiple of 16, so every item has the same phase
   // Choose strips per item (ns) and vertical parts per column with a small cost model:
   // a CTA's time ~ (items it owns) x (chunks per item) x (instructions per task) / warps.
@@ -545,14 +658,19 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   const int nc = 2 * g.R + 1;
   double best_cost = 1e300;
   int best_ns = 0, best_parts = 1;
+  constexpr int BWc = SW / NSUB;
+  const int e_s = (4 - (g.R % 4)) % 4;  // SW is a multiple of 4 elements: same phase for every item
+  auto s_pitch_of = [&](int ns) { return (e_s + ns * SW + 2 * g.R - BWc + 1 + 3) & ~3; };
   auto stage_size = [&](int ns) {
     const int wb = kWinPitch;
     const int win = ((wb * p.wh) + 127) & ~127;
-    return (win + ns * SW * BH + ns * NSUB * 8 + 127) & ~127;
+    const int stile = FORM == 2 ? ((s_pitch_of(ns) * (2 * g.R + 1) * 4 + 127) & ~127) : 0;
+    return (win + ns * SW * BH + stile + ns * NSUB * 8 + 127) & ~127;
   };
   for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
     const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
     if (wb > 256 || ns * SW > 256) break;
+    if (FORM == 2 && s_pitch_of(ns) > 256) break;
     if (2 * stage_size(ns) + static_smem > plan->max_smem) break;
     if (plan->ns_override > 0 && ns != plan->ns_override) continue;
     const long long items = rows_total * ((p.strips_per_row + ns - 1) / ns);
@@ -568,7 +686,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       // per task: L candidates x BH rows x WORDS cross-term ops (x2 for FORM 0), plus per streamed
       // row the loads, shifts and (FORM 1) the row-energy ops
       const double per_row = FORM == 1 ? (2.0 * WORDS + 8.0) : (2.0 * WORDS + 6.0);
-      const double task = (double)L * BH * WORDS * (FORM == 1 ? 1.0 : 2.0) + (double)(L + BH - 1) * per_row + 250.0;
+      const double task = (double)L * BH * WORDS * (FORM >= 1 ? 1.0 : 2.0) + (double)(L + BH - 1) * per_row + 250.0;
       // warps flow from one item into the next, so chunks only quantise over the CTA's whole run
       const double cost = (double)((per_cta * chunks + kWarps - 1) / kWarps) * task + 0.02 * per_cta * 2000.0;
       if (cost < best_cost * 0.999) { best_cost = cost; best_ns = ns; best_parts = parts; }
@@ -584,6 +702,10 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.e = ebytes;
   p.win_bytes = ((p.wb * p.wh) + 127) & ~127;
   p.cur_pitch = ns * SW;
+  p.s_pitch = s_pitch_of(ns);
+  p.s_rows = 2 * g.R + 1;
+  p.s_bytes = (p.s_pitch * p.s_rows * 4 + 127) & ~127;
+  p.e_s = e_s;
   p.stage_bytes = stage_size(ns);
   p.stages = (plan->max_smem - static_smem) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -613,14 +735,72 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     *err = msg;
     return cudaErrorInvalidValue;
   }
+  // FORM 2: build the energy tables for the rows this launch needs (stream-ordered scratch)
+  CUtensorMap map_s = map_ref, map_sh = map_ref;  // placeholders for the other formulations
+  uint32_t *d_s = nullptr;
+  if (FORM == 2) {
+    constexpr int BW = SW / NSUB;
+    const int tp = (g.W + 3) & ~3;  // table pitch in elements
+    const int full_rows = g.H / g.B;
+    const int last_full = (by_begin + by_count < full_rows ? by_begin + by_count : full_rows) - 1;
+    int y_lo = by_begin * g.B - g.R, y_hi = last_full * g.B + g.R;
+    if (y_lo < 0) y_lo = 0;
+    if (y_hi > g.H - BH) y_hi = g.H - BH;
+    const int nfull = (by_begin < full_rows && y_hi >= y_lo) ? y_hi - y_lo + 1 : 0;
+    const bool has_half = by_begin + by_count > full_rows;  // the bottom row of height BH/2
+    const int nhalf = has_half ? g.R + 1 : 0;
+    const size_t per_pair = (size_t)tp * (size_t)(nfull + nhalf);
+    cudaError_t e = cudaMallocAsync((void **)&d_s, per_pair * 4 * (size_t)npairs + 256, s);
+    if (e != cudaSuccess) { *err = "cudaMallocAsync(energy table)"; return e; }
+    const size_t ref_pair_stride = npairs > 1 ? f.pair_stride : f.pitch * g.H;
+    if (nfull > 0) {
+      dim3 eg((tp + kEx - 1) / kEx, (nfull + kEy - 1) / kEy, npairs);
+      box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH, y_lo, nfull, d_s, tp,
+                                           per_pair);
+    }
+    if (nhalf > 0) {
+      dim3 eg((tp + kEx - 1) / kEx, (nhalf + kEy - 1) / kEy, npairs);
+      box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH / 2,
+                                           g.H - BH / 2 - g.R, nhalf, d_s + (size_t)tp * nfull, tp, per_pair);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = "box_energy_kernel launch"; cudaFreeAsync(d_s, s); return e; }
+    p.s_y0 = y_lo;
+    const cuuint64_t sstr[2] = {(cuuint64_t)tp * 4, (cuuint64_t)per_pair * 4};
+    const cuuint32_t sbox[3] = {(cuuint32_t)p.s_pitch, (cuuint32_t)p.s_rows, 1};
+    CUresult r3 = CUDA_SUCCESS, r4 = CUDA_SUCCESS;
+    if (nfull > 0) {
+      const cuuint64_t sd[3] = {(cuuint64_t)tp, (cuuint64_t)nfull, (cuuint64_t)npairs};
+      r3 = enc(&map_s, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)d_s, sd, sstr, sbox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (nhalf > 0) {
+      const cuuint64_t sd[3] = {(cuuint64_t)tp, (cuuint64_t)nhalf, (cuuint64_t)npairs};
+      r4 = enc(&map_sh, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)(d_s + (size_t)tp * nfull), sd, sstr, sbox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r3 != CUDA_SUCCESS || r4 != CUDA_SUCCESS) {
+      *err = "cuTensorMapEncodeTiled(energy table) failed";
+      cudaFreeAsync(d_s, s);
+      return cudaErrorInvalidValue;
+    }
+    if (nfull == 0) map_s = map_sh;
+    if (nhalf == 0) map_sh = map_s;
+  }
   const int smem = p.stages * p.stage_bytes;
+  if (getenv("ME_B200_VERBOSE"))
+    fprintf(stderr, "[me_b200] tiled<%d,%d,%d,form %d> ns=%d parts=%d items=%d stages=%d stage=%d B smem=%d B s_pitch=%d\n",
+            WORDS, BH, NSUB, FORM, p.ns, p.parts_target, p.total_items, p.stages, p.stage_bytes, smem, p.s_pitch);
   auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; return e; }
+  if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; if (d_s) cudaFreeAsync(d_s, s); return e; }
   const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
-  kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, p);
+  kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
+  if (d_s) cudaFreeAsync(d_s, s);
   return e;
 }
 
@@ -629,9 +809,21 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
                          int by_begin, int by_count, cudaStream_t s, const char **err) {
   // PW: the frame width is not a multiple of the strip width, so the last strip holds a
   // partial-width block whose out-of-block reference bytes must be masked (FORM 1 only)
-  if (FORM == 1 && (g.W % (4 * WORDS)) != 0)
-    return launch_shape_pw<WORDS, BH, NSUB, FORM, true>(plan, g, f, npairs, o, by_begin, by_count, s, err);
-  return launch_shape_pw<WORDS, BH, NSUB, FORM, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+  if constexpr (FORM == 1) {
+    if ((g.W % (4 * WORDS)) != 0)
+      return launch_shape_pw<WORDS, BH, NSUB, 1, true>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+  }
+  if constexpr (FORM == 2) {
+    // the energy table only knows full-width blocks, and its tile must fit the stage twice
+    if (g.W % (4 * WORDS / NSUB) == 0) {
+      cudaError_t e = launch_shape_pw<WORDS, BH, NSUB, 2, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+      if (e != cudaErrorInvalidConfiguration) return e;
+      (void)cudaGetLastError();
+    }
+    return launch_shape<WORDS, BH, NSUB, 1>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+  } else {
+    return launch_shape_pw<WORDS, BH, NSUB, FORM, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+  }
 }
 
 }  // namespace
@@ -643,12 +835,15 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   // as a one-row band.
   const int full_rows = g.H / g.B;
   const int hrem = g.H % g.B;
-  const int tiled_rows = full_rows + ((plan->form == 1 && hrem == g.B / 2) ? 1 : 0);
+  const int tiled_rows = full_rows + ((plan->form >= 1 && hrem == g.B / 2) ? 1 : 0);
   const int r0 = g.by_begin, r1 = g.by_begin + g.by_count;
   const int t1 = r1 < tiled_rows ? r1 : tiled_rows;
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
-    if (plan->form == 1) {
+    if (plan->form == 2) {
+      if (g.B == 16) e = launch_shape<4, 16, 1, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+      else e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+    } else if (plan->form == 1) {
       if (g.B == 16) e = launch_shape<4, 16, 1, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
       else e = launch_shape<4, 8, 2, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
     } else {
