@@ -336,6 +336,12 @@ def main():
         achieved = lane_instr / step_s
         alg_bytes = pairs * (2 * W * H + 16 * nb)                # u8 cur + ref read once, 16 B/block out
         clocks = sampler.summary()
+        traffic = None   # DRAM bytes of the search kernel per launch, from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)[name]["bytes_per_pair"] * pairs
+        except Exception:
+            pass
         line = {
             "metric": METRIC if name == "1080p_16x16_pm32" else name + "_frames_per_sec",
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -353,7 +359,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": pair_rate / 1e12,
                          "unit": "T lane-instr/s", "frac": achieved / pair_rate if pair_rate else None,
-                         "traffic": None,
+                         "traffic": traffic,
                          "peak_source": "measured live: me_b200_int_peak(VABSDIFF4+IDP.4A pairs) at %.0f MHz" % mhz,
                          "frac_of_single_pipe_peak": achieved / (pair_rate / 2) if pair_rate else None,
                          "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": 6455.9,

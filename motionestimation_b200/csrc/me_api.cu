@@ -300,11 +300,17 @@ int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t
   int rc = use_device(ctx);
   if (rc) return rc;
   const size_t W = (size_t)ctx->g.W, H = (size_t)ctx->g.H;
-  // pairs are contiguous on the host (stride W) and on the device (pitch): one 2-D copy each
-  ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs,
-                                 cudaMemcpyHostToDevice, s.stream));
-  ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs,
-                                 cudaMemcpyHostToDevice, s.stream));
+  // pairs are contiguous on the host (stride W) and on the device (pitch): one copy per frame
+  // set -- linear when the device pitch equals the width (no per-row DMA descriptors), 2-D otherwise
+  if (ctx->pitch == W) {
+    ME_CUDA(ctx, cudaMemcpyAsync(s.d_cur, cur, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream));
+    ME_CUDA(ctx, cudaMemcpyAsync(s.d_ref, ref, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs,
+                                   cudaMemcpyHostToDevice, s.stream));
+    ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs,
+                                   cudaMemcpyHostToDevice, s.stream));
+  }
   me::Frames f{s.d_cur, s.d_ref, ctx->pitch, ctx->frame_bytes};
   me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
   rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
