@@ -86,9 +86,20 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
   if (tiled) {
     const char *txt = nullptr;
     cudaError_t e = me::launch_tiled(ctx->plan, g, f, npairs, o, s, &txt);
-    if (e != cudaSuccess) return fail_cuda(ctx, e, txt ? txt : "launch_tiled");
-  } else {
-    // grid.y carries the pair index
+    if (e == cudaErrorInvalidConfiguration && ctx->kernel_req != ME_KERNEL_TILED) {
+      // the geometry does not fit the tuned kernel's shared-memory ring: same results, generic kernel
+      (void)cudaGetLastError();
+      tiled = false;
+    } else if (e != cudaSuccess) {
+      return fail_cuda(ctx, e, txt ? txt : "launch_tiled");
+    }
+  }
+  if (tiled) {
+    ctx->launches++;
+    return ME_OK;
+  }
+  {
+    // generic kernel; grid.y carries the pair index
     int done = 0;
     while (done < npairs) {
       int n = npairs - done > 65535 ? 65535 : npairs - done;
@@ -106,9 +117,7 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
       ctx->launches++;
       done += n;
     }
-    return ME_OK;
   }
-  ctx->launches++;
   return ME_OK;
 }
 

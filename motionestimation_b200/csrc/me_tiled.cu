@@ -106,9 +106,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -594,7 +591,9 @@ static int env_form() {
 bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
   if (!shape_ok(g.B)) return false;
   if (env_form() == 0 && g.W % g.B != 0) return false;  // FORM 0 has no partial-width blocks
-  if (g.R < 0 || g.R > 120) return false;     // key packs dy in 8 bits; TMA box <= 256 rows
+  if (g.R < 0 || 2 * g.R + g.B > 256) return false;  // key packs dy in 8 bits; TMA box <= 256 rows
+  // one strip (16 px) plus the span plus the alignment slack must fit the 256-byte window row
+  if ((16 - g.R % 16) % 16 + 16 + 2 * g.R + 4 > kWinPitch) return false;
   if (g.W < g.B || g.H < g.B) return false;
   if ((pitch & 15) || (pair_stride & 15)) return false;  // TMA: 16-byte aligned base and strides
   if (((uintptr_t)cur & 15) || ((uintptr_t)ref & 15)) return false;

@@ -53,6 +53,9 @@ RANDOM_GEOMS = [
     (8, 32, 128, 72), (4, 15, 33, 29), (5, 7, 41, 23), (7, 1, 30, 30), (32, 15, 80, 72),
     (64, 7, 130, 70), (8, 0, 32, 32), (3, 2, 7, 5), (16, 32, 16, 16), (8, 12, 8, 8), (16, 8, 48, 40),
     (16, 32, 208, 56), (8, 4, 72, 40), (16, 16, 64, 64), (8, 8, 352, 16),
+    # spans that are not multiples of 4 / 16 (TMA origin phases), odd block counts, half-height bottom rows
+    (16, 7, 96, 64), (8, 5, 64, 48), (16, 33, 128, 104), (8, 13, 88, 60), (16, 1, 48, 40), (8, 2, 24, 20),
+    (16, 120, 64, 48), (16, 121, 64, 48), (8, 64, 96, 72), (16, 9, 336, 24),
 ]
 
 
