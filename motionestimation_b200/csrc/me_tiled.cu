@@ -338,7 +338,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       const int m_uni = __reduce_max_sync(0xffffffffu, I.m);
       // FORM 2: energy-table entry of the candidate that finishes at step 0 of the current period
       // (only dereferenced for candidates that exist)
-      const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * p.s_pitch +
+      const int s_pitch = p.s_pitch;
+      const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * s_pitch +
                             p.e_s + st * SW + dx;
       for (int per = 0; per <= m_uni; per++) {
         const bool first = per == 0;
@@ -401,7 +402,11 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
                 // candidate complete: fold (ssd << 8 | dy) into the running minimum
                 uint32_t ssd = a;
                 if (FORM == 1) ssd = srun[b] - 2u * a;
-                if (FORM == 2) ssd = srun[b] + spf[s_ * p.s_pitch + b * BW] - 2u * a;
+                if (FORM == 2) {
+                  // (A + E) - a - a: one IADD3 on the ALU pipe instead of an IMAD on the saturated FMA pipe
+                  const uint32_t ae = srun[b] + spf[b * BW];
+                  asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %2; }" : "=r"(ssd) : "r"(ae), "r"(a));
+                }
                 const uint32_t key = (ssd << 8) + (uint32_t)(dy_fin + s_);
                 bestk[b] = min(bestk[b], key);
               }
@@ -426,9 +431,9 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           }
           group(s_);
 #endif
+          if (FORM == 2) spf += s_pitch;  // next step finishes the candidate one row further down
         }
         dy_fin += BH;
-        if (FORM == 2) spf += BH * p.s_pitch;
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
