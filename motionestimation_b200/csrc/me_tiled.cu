@@ -96,6 +96,7 @@ struct TiledParams {
   int s_bytes;            // FORM 2: tile bytes rounded up to 128
   int e_s;                // FORM 2: elements between the 4-aligned TMA origin and x0-R
   int s_y0;               // FORM 2: frame row of the table's first row
+  unsigned int *next_item; // global work counter of this launch (zeroed on the stream before it)
   Out out;
 };
 
@@ -185,25 +186,38 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];  // TMA bytes of the stage's item have landed
   __shared__ uint32_t chunk_ctr[kMaxStages];              // next 32-task chunk of the stage's item
   __shared__ uint32_t left_ctr[kMaxStages];               // warps that are done with the stage's item
+  __shared__ int item_id[kMaxStages];                     // item held by the stage, -1 = no more work
 
   const int lane = threadIdx.x & 31;
   const int cur_off = p.win_bytes;                       // byte offsets inside a stage
   const int s_off = p.win_bytes + p.cur_pitch * BH;      // FORM 2: energy tile
   const int best_off = s_off + (FORM == 2 ? p.s_bytes : 0);
-  const int grid = (int)gridDim.x;
-  const int nmine = p.total_items > (int)blockIdx.x ? (p.total_items - (int)blockIdx.x + grid - 1) / grid : 0;
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
-  // (re)arm a stage with this CTA's k-th item: reset its keys and counters, start the TMA.
-  // Called by one whole warp.
-  auto refill = [&](const int stage, const int k) {
+  // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
+  // row-major order, so the cheap clamped/half-height bottom rows come last and the tail is
+  // short), reset the stage's keys and counters and start the TMA.  When the work is exhausted the
+  // stage is marked dead and its barrier completed without a load.  Called by one whole warp.
+  auto refill = [&](const int stage) {
     uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
-    const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(p.next_item, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= p.total_items) {
+      if (lane == 0) {
+        item_id[stage] = -1;
+        mbar_arrive_expect_tx(&full_bar[stage], 0);
+      }
+      __syncwarp();
+      return;
+    }
+    const Item I = decode_item<BH>(p, it);
     for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
     if (lane == 0) {
       chunk_ctr[stage] = 0;
       left_ctr[stage] = 0;
+      item_id[stage] = it;
     }
     __syncwarp();
     if (lane == 0) {
@@ -234,7 +248,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   }
   __syncthreads();
   if (threadIdx.x < 32)
-    for (int k = 0; k < p.stages && k < nmine; k++) refill(k, k);
+    for (int k = 0; k < p.stages; k++) refill(k);
 
   // Stagger the warps that share a scheduler (warp & 3): they run identical instruction
   // streams at the same pipe-bound rate, so without a stagger they reach the non-IDP section
@@ -245,12 +259,21 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     }
   }
 
-  for (int k = 0; k < nmine; k++) {
+  // Every warp walks the ring; a stage that reported "no more work" is never re-armed and is
+  // skipped from then on; the walk ends when all stages are dead.
+  uint32_t dead = 0;
+  for (int k = 0; dead != (1u << p.stages) - 1u; k++) {
     const int stage = k % p.stages;
+    if (dead & (1u << stage)) continue;
     uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
-    const Item I = decode_item<BH>(p, (int)blockIdx.x + k * grid);
     mbar_wait(&full_bar[stage], (k / p.stages) & 1);
+    const int it = *reinterpret_cast<volatile int *>(&item_id[stage]);
+    if (it < 0) {
+      dead |= 1u << stage;
+      continue;
+    }
+    const Item I = decode_item<BH>(p, it);
 
     const int L = I.m * BH + 1;
     const int ndx = 2 * p.R + 1;
@@ -477,7 +500,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         }
       }
       __syncwarp();
-      if (k + p.stages < nmine) refill(stage, k + p.stages);
+      refill(stage);
     }
   }
 }
@@ -582,6 +605,7 @@ struct TiledPlan {
   int max_smem = 0;
   int parts_target = 0;
   int ns_override = 0;
+  bool form_env_forced = false;  // ME_B200_FORM=2: use the table even for tiny launches (tests)
   int form = 2;  // 2: energy table when possible, else 1 (default); 1: on-the-fly energies;
                  // 0: |a-b|^2 -- env ME_B200_FORM selects 0/1 for A/B measurements
 };
@@ -611,6 +635,10 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
   if (!shape_ok(g.B)) return cudaErrorNotSupported;
   TiledPlan *pl = new TiledPlan();
   pl->form = env_form();
+  {
+    const char *f = getenv("ME_B200_FORM");
+    pl->form_env_forced = f && f[0] == '2';
+  }
 
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -793,18 +821,37 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     if (nfull == 0) map_s = map_sh;
     if (nhalf == 0) map_sh = map_s;
   }
+  // launch-wide work counter (stream-ordered scratch, zeroed on the stream)
+  unsigned int *d_ctr = nullptr;
+  {
+    cudaError_t ce = cudaMallocAsync((void **)&d_ctr, 256, s);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_ctr, 0, 256, s);
+    if (ce != cudaSuccess) {
+      *err = "cudaMallocAsync(work counter)";
+      if (d_s) cudaFreeAsync(d_s, s);
+      if (d_ctr) cudaFreeAsync(d_ctr, s);
+      return ce;
+    }
+    p.next_item = d_ctr;
+  }
   const int smem = p.stages * p.stage_bytes;
   if (getenv("ME_B200_VERBOSE"))
     fprintf(stderr, "[me_b200] tiled<%d,%d,%d,form %d> ns=%d parts=%d items=%d stages=%d stage=%d B smem=%d B s_pitch=%d\n",
             WORDS, BH, NSUB, FORM, p.ns, p.parts_target, p.total_items, p.stages, p.stage_bytes, smem, p.s_pitch);
   auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(tiled)"; if (d_s) cudaFreeAsync(d_s, s); return e; }
+  if (e != cudaSuccess) {
+    *err = "cudaFuncSetAttribute(tiled)";
+    if (d_s) cudaFreeAsync(d_s, s);
+    cudaFreeAsync(d_ctr, s);
+    return e;
+  }
   const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
   kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
   if (d_s) cudaFreeAsync(d_s, s);
+  cudaFreeAsync(d_ctr, s);
   return e;
 }
 
@@ -844,10 +891,12 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   const int t1 = r1 < tiled_rows ? r1 : tiled_rows;
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
-    if (plan->form == 2) {
+    // the energy-table pre-pass (two small launches) only pays off once there is enough work
+    const bool table = plan->form == 2 && (long long)npairs * g.W * g.H >= (plan->form_env_forced ? 0 : 2000000LL);
+    if (table) {
       if (g.B == 16) e = launch_shape<4, 16, 1, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
       else e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
-    } else if (plan->form == 1) {
+    } else if (plan->form >= 1) {
       if (g.B == 16) e = launch_shape<4, 16, 1, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
       else e = launch_shape<4, 8, 2, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
     } else {

@@ -59,6 +59,16 @@ RANDOM_GEOMS = [
 ]
 
 
+# tuned-kernel formulations (env ME_B200_FORM, read when the context is created): default = energy
+# table for big launches / on-the-fly energies for small ones; "2" forces the table, "1" forces
+# on-the-fly, "0" = VABSDIFF4 + IDP.4A
+@pytest.mark.parametrize("form", ["2", "1", "0"])
+@pytest.mark.parametrize("B,R,W,H", RANDOM_GEOMS)
+def test_random_differential_formulations(orc, monkeypatch, B, R, W, H, form):
+    monkeypatch.setenv("ME_B200_FORM", form)
+    test_random_differential(orc, B, R, W, H, me.ME_KERNEL_AUTO)
+
+
 @pytest.mark.parametrize("kernel", KERNELS, ids=["generic", "auto"])
 @pytest.mark.parametrize("B,R,W,H", RANDOM_GEOMS)
 def test_random_differential(orc, B, R, W, H, kernel):
@@ -124,6 +134,12 @@ def test_cli_is_byte_identical(tmp_path, args, name):
 def _torch():
     import torch
     return torch
+
+
+@pytest.mark.parametrize("form", ["2", "1"])
+def test_device_path_bands_formulations(orc, monkeypatch, form):
+    monkeypatch.setenv("ME_B200_FORM", form)
+    test_device_path_bands_and_batches(orc, me.ME_KERNEL_AUTO)
 
 
 @pytest.mark.parametrize("kernel", KERNELS, ids=["generic", "auto"])
