@@ -113,6 +113,17 @@ int me_b200_search_u8(me_b200_ctx *ctx, const uint8_t *cur, const uint8_t *ref, 
 int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t *ref, int npairs,
                    int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
 int me_b200_wait(me_b200_ctx *ctx, int slot);
+/* ---- sequences ----------------------------------------------
+ * nframes consecutive frames of one video (u8, stride == width, frame i at frames + i*W*H),
+ * 2 <= nframes <= max_pairs + 1.  Pair i searches frame i+1 (current) in frame i (reference),
+ * i.e. the reference program run on every consecutive pair (argv[1] = frame i+1, argv[2] =
+ * frame i, main.c:114-115).  Each frame crosses PCIe once and is used as the current frame of
+ * one pair and the reference frame of the next.  Outputs: (nframes-1)*num_blocks entries.
+ * me_b200_submit_sequence is asynchronous on the slot's stream (pair with me_b200_wait). */
+int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, int nframes,
+                            int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
+int me_b200_search_sequence_u8(me_b200_ctx *ctx, const uint8_t *frames, int nframes,
+                               int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
 void *me_b200_host_alloc(size_t bytes); /* pinned; NULL on failure */
 void  me_b200_host_free(void *p);
 

@@ -94,10 +94,7 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
       return fail_cuda(ctx, e, txt ? txt : "launch_tiled");
     }
   }
-  if (tiled) {
-    ctx->launches++;
-    return ME_OK;
-  }
+  if (tiled) return ME_OK;  // counted by the plan (search kernel + pre-pass kernels)
   {
     // generic kernel; grid.y carries the pair index
     int done = 0;
@@ -202,7 +199,7 @@ int me_b200_create_ex(me_b200_ctx **out, int device, int width, int height, int 
       rc = ce == cudaErrorMemoryAllocation ? ME_ERR_NOMEM : ME_ERR_CUDA;
     }
   };
-  const size_t fb = ctx->frame_bytes * (size_t)max_pairs + 256;  // tail slack for TMA boxes
+  const size_t fb = ctx->frame_bytes * ((size_t)max_pairs + 1) + 256;  // +1 frame: sequences; tail slack
   const size_t ob = (size_t)ctx->nb * (size_t)max_pairs;
   for (int i = 0; i < ME_B200_MAX_SLOTS && rc == ME_OK; i++) {
     me_slot &s = ctx->slots[i];
@@ -286,7 +283,9 @@ uint64_t me_b200_candidates(const me_b200_ctx *ctx) {
   if (!ctx) return 0;
   return axis_sum(ctx->g.W, ctx->g.B, ctx->g.R, false) * axis_sum(ctx->g.H, ctx->g.B, ctx->g.R, false);
 }
-uint64_t me_b200_launch_count(const me_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t me_b200_launch_count(const me_b200_ctx *ctx) {
+  return ctx ? ctx->launches + me::tiled_plan_launches(ctx->plan) : 0;
+}
 
 void *me_b200_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -331,6 +330,68 @@ int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t
   if (score) ME_CUDA(ctx, cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream));
   s.busy = true;
   return ME_OK;
+}
+
+int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, int nframes, int32_t *mvx,
+                            int32_t *mvy, uint32_t *ssd, float *score) {
+  if (!ctx || !frames || slot < 0 || slot >= ME_B200_MAX_SLOTS) return ME_ERR_INVALID_ARG;
+  if (nframes < 2 || nframes - 1 > ctx->max_pairs) return ME_ERR_INVALID_ARG;
+  me_slot &s = ctx->slots[slot];
+  if (s.busy) return ME_ERR_STATE;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  const size_t W = (size_t)ctx->g.W, H = (size_t)ctx->g.H;
+  // every frame is uploaded once into the slot's frame buffer
+  if (ctx->pitch == W) {
+    ME_CUDA(ctx, cudaMemcpyAsync(s.d_cur, frames, W * H * (size_t)nframes, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_cur, ctx->pitch, frames, W, W, H * (size_t)nframes,
+                                   cudaMemcpyHostToDevice, s.stream));
+  }
+  // pair i: current = frame i+1, reference = frame i -- two views of the same buffer
+  const int npairs = nframes - 1;
+  me::Frames f{s.d_cur + ctx->frame_bytes, s.d_cur, ctx->pitch, ctx->frame_bytes};
+  me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
+  rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
+  if (rc) return rc;
+  const size_t ob = (size_t)ctx->nb * (size_t)npairs * 4;
+  if (mvx) ME_CUDA(ctx, cudaMemcpyAsync(mvx, s.d_mvx, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (mvy) ME_CUDA(ctx, cudaMemcpyAsync(mvy, s.d_mvy, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (ssd) ME_CUDA(ctx, cudaMemcpyAsync(ssd, s.d_ssd, ob, cudaMemcpyDeviceToHost, s.stream));
+  if (score) ME_CUDA(ctx, cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream));
+  s.busy = true;
+  return ME_OK;
+}
+
+int me_b200_search_sequence_u8(me_b200_ctx *ctx, const uint8_t *frames, int nframes, int32_t *mvx,
+                               int32_t *mvy, uint32_t *ssd, float *score) {
+  if (!ctx || !frames || nframes < 2) return ME_ERR_INVALID_ARG;
+  // longer sequences go through in chunks of max_pairs pairs; consecutive chunks share one frame
+  const size_t fsz = (size_t)ctx->g.W * ctx->g.H;
+  int first = 0, k = 0, rc = ME_OK;
+  int inflight[ME_B200_MAX_SLOTS] = {0, 0, 0, 0};
+  while (first < nframes - 1 && rc == ME_OK) {
+    const int slot = k % ME_B200_MAX_SLOTS;
+    if (inflight[slot]) {
+      rc = me_b200_wait(ctx, slot);
+      inflight[slot] = 0;
+      if (rc) break;
+    }
+    int np = nframes - 1 - first;
+    if (np > ctx->max_pairs) np = ctx->max_pairs;
+    const size_t oo = (size_t)first * ctx->nb;
+    rc = me_b200_submit_sequence(ctx, slot, frames + (size_t)first * fsz, np + 1, mvx ? mvx + oo : nullptr,
+                                 mvy ? mvy + oo : nullptr, ssd ? ssd + oo : nullptr, score ? score + oo : nullptr);
+    if (rc == ME_OK) inflight[slot] = 1;
+    first += np;
+    k++;
+  }
+  for (int i = 0; i < ME_B200_MAX_SLOTS; i++)
+    if (inflight[i]) {
+      int r2 = me_b200_wait(ctx, i);
+      if (rc == ME_OK) rc = r2;
+    }
+  return rc;
 }
 
 int me_b200_wait(me_b200_ctx *ctx, int slot) {

@@ -39,6 +39,7 @@ bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void
 struct TiledPlan;  // opaque: tensor maps + launch shape
 cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int max_pairs);
 void tiled_plan_destroy(TiledPlan *plan);
+unsigned long long tiled_plan_launches(const TiledPlan *plan);  // kernels launched so far
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err_text);
 

@@ -605,6 +605,7 @@ struct TiledPlan {
   int max_smem = 0;
   int parts_target = 0;
   int ns_override = 0;
+  unsigned long long kernels_launched = 0;  // every kernel this plan has launched (search + pre-pass)
   bool form_env_forced = false;  // ME_B200_FORM=2: use the table even for tiny launches (tests)
   int form = 2;  // 2: energy table when possible, else 1 (default); 1: on-the-fly energies;
                  // 0: |a-b|^2 -- env ME_B200_FORM selects 0/1 for A/B measurements
@@ -666,6 +667,7 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
 }
 
 void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
+unsigned long long tiled_plan_launches(const TiledPlan *plan) { return plan ? plan->kernels_launched : 0; }
 
 namespace {
 
@@ -789,11 +791,13 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       dim3 eg((tp + kEx - 1) / kEx, (nfull + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH, y_lo, nfull, d_s, tp,
                                            per_pair);
+      plan->kernels_launched++;
     }
     if (nhalf > 0) {
       dim3 eg((tp + kEx - 1) / kEx, (nhalf + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH / 2,
                                            g.H - BH / 2 - g.R, nhalf, d_s + (size_t)tp * nfull, tp, per_pair);
+      plan->kernels_launched++;
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) { *err = "box_energy_kernel launch"; cudaFreeAsync(d_s, s); return e; }
@@ -848,6 +852,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   }
   const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
   kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
+  plan->kernels_launched++;
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
   if (d_s) cudaFreeAsync(d_s, s);
@@ -910,6 +915,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
     gb.by_begin = r0 > tiled_rows ? r0 : tiled_rows;
     gb.by_count = r1 - gb.by_begin;
     e = launch_generic(gb, f, npairs, o, s);
+    plan->kernels_launched++;
     if (e != cudaSuccess) *err = "launch_generic(partial bottom row)";
   }
   return e;

@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
         "me_b200_search_u8": (C.c_int, [vp, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_submit": (C.c_int, [vp, C.c_int, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_wait": (C.c_int, [vp, C.c_int]),
+        "me_b200_submit_sequence": (C.c_int, [vp, C.c_int, u8p, C.c_int, i32p, i32p, u32p, f32p]),
+        "me_b200_search_sequence_u8": (C.c_int, [vp, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_host_alloc": (vp, [C.c_size_t]),
         "me_b200_host_free": (None, [vp]),
         "me_b200_search_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int,
@@ -216,6 +218,27 @@ class Estimator:
                                                 _np_ptr(out["ssd"]), _np_ptr(out["score"])),
                     "me_b200_search_u8")
         return out
+
+    def search_sequence_u8(self, frames: np.ndarray):
+        """Consecutive pairs of a frame sequence (nframes, H, W): pair i = frame i+1 searched in
+        frame i; every frame is uploaded once.  Returns dict of (nframes-1, num_blocks) arrays."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = self.width * self.height
+        if frames.size % n or frames.size // n < 2:
+            raise ValueError("frames must be nframes x H x W uint8, nframes >= 2")
+        nframes = frames.size // n
+        out = self._alloc_out(nframes - 1)
+        self._check(self._lib.me_b200_search_sequence_u8(self._h, _np_ptr(frames), nframes,
+                                                         _np_ptr(out["mvx"]), _np_ptr(out["mvy"]),
+                                                         _np_ptr(out["ssd"]), _np_ptr(out["score"])),
+                    "me_b200_search_sequence_u8")
+        return out
+
+    def submit_sequence_ptr(self, slot: int, frames_ptr: int, nframes: int, mvx_ptr: int, mvy_ptr: int,
+                            ssd_ptr: int, score_ptr: int):
+        self._check(self._lib.me_b200_submit_sequence(self._h, slot, frames_ptr, nframes, mvx_ptr, mvy_ptr,
+                                                      ssd_ptr or None, score_ptr or None),
+                    "me_b200_submit_sequence")
 
     def _alloc_out(self, npairs: int):
         nb = self.num_blocks

@@ -239,6 +239,20 @@ def test_pipelined_submit_wait():
         assert ei.value.code == me.ME_ERR_STATE
 
 
+@pytest.mark.parametrize("B,R,max_pairs", [(8, 12, 4), (16, 32, 2), (16, 32, 8)])
+def test_sequence_shares_frames(orc, B, R, max_pairs):
+    """me_b200_search_sequence_u8: pair i = frame i+1 searched in frame i, each frame uploaded
+    once, long sequences chunked by max_pairs -- identical to independent pairs."""
+    seq = np.stack([me.foreman(1), me.foreman(2), me.foreman(4), me.foreman(2), me.foreman(1), me.foreman(4),
+                    me.foreman(1)])
+    with me.Estimator(352, 288, B, R, max_pairs=max_pairs) as est:
+        out = est.search_sequence_u8(seq)
+    assert out["mvx"].shape == (len(seq) - 1, (352 // B) * (288 // B))
+    for i in range(len(seq) - 1):
+        o = orc.search(seq[i + 1], seq[i], B, R)
+        check_against(out, i, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {i}")
+
+
 def recompute_ssd(cur, ref, B, mvx, mvy):
     """SSD of the chosen candidates from the frames alone (numpy)."""
     H, W = cur.shape
