@@ -308,6 +308,34 @@ def test_full_size_properties(orc, W, H, B, R):
         assert np.array_equal(g["score"][0].view(np.uint32), out["score"][1].view(np.uint32))
 
 
+def test_repeatability_under_load():
+    """The chunk/item scheduling is dynamic (atomics decide who scores what); results must not
+    depend on it: 30 back-to-back batched searches return bit-identical fields."""
+    torch = _torch()
+    W, H, B, R, P = 1920, 1080, 16, 32, 4
+    frames = [me.tiled_frames(W, H, 2, 1), me.shifted_noise_pair(W, H, seed=5), me.tiled_frames(W, H, 4, 2),
+              me.random_pair(W, H, 9)]
+    cur = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    ref = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    with me.Estimator(W, H, B, R, max_pairs=P) as est:
+        nb = est.num_blocks
+        outs = []
+        for it in range(30):
+            mvx = torch.zeros((P, nb), dtype=torch.int32, device="cuda")
+            mvy = torch.zeros_like(mvx)
+            ssd = torch.zeros_like(mvx)
+            est.search_device(cur, ref, W, W * H, P, mvx, mvy, ssd)
+            outs.append((mvx, mvy, ssd))
+        torch.cuda.synchronize()
+        for mvx, mvy, ssd in outs[1:]:
+            assert torch.equal(mvx, outs[0][0]) and torch.equal(mvy, outs[0][1]) and torch.equal(ssd, outs[0][2])
+        # and they are the right answer: recomputed SSD at the reported MVs
+        mv = (outs[0][0].cpu().numpy(), outs[0][1].cpu().numpy(), outs[0][2].cpu().numpy())
+        for p in range(P):
+            assert np.array_equal(recompute_ssd(frames[p][0], frames[p][1], B, mv[0][p], mv[1][p]),
+                                  mv[2][p].astype(np.int64))
+
+
 def test_int_peak_microbenchmarks_run():
     for which in (0, 1, 2):
         rate, mhz = me.int_peak(which, iters=200)
