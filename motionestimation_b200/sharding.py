@@ -71,32 +71,41 @@ def row_costs(width: int, height: int, blk_dim: int, extra_span: int) -> List[in
     return [sx * c for c in axis(height)]
 
 
-def gather_bands(local: "torch.Tensor", rows: Tuple[int, int], nby: int, nbx: int, group=None):
-    """All-gather the per-band slices of a field.
+def all_band_rows(nby: int, world: int, weights: Optional[Sequence[float]] = None) -> List[Tuple[int, int]]:
+    """The bands of every rank (each rank can compute all of them: no collective needed)."""
+    return [band_rows(nby, world, r, weights) for r in range(world)]
 
-    `local` is this rank's (npairs, (rows[1]-rows[0]) * nbx) tensor (any dtype,
-    CUDA for NCCL, CPU for gloo).  Returns the full (npairs, nby * nbx) field on
-    every rank.  Bands may have different heights, so slices are padded to the
-    tallest band for the collective and trimmed afterwards.
+
+def gather_bands(local: "torch.Tensor", rows: Tuple[int, int], nby: int, nbx: int, group=None,
+                 spans: Optional[List[Tuple[int, int]]] = None):
+    """All-gather the per-band slices of a field with ONE collective.
+
+    `local` is this rank's (..., (rows[1]-rows[0]) * nbx) tensor (any leading dims, any dtype,
+    CUDA for NCCL, CPU for gloo).  Returns the full (..., nby * nbx) field on every rank.
+    Bands may have different heights, so slices are padded to the tallest band for the
+    collective and trimmed afterwards.  `spans` = the bands of all ranks when the caller already
+    knows them (they follow from `band_rows`); otherwise they are exchanged first.
     """
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    npairs = local.shape[0]
-    mine = torch.tensor([rows[0], rows[1]], dtype=torch.int64, device=local.device)
-    all_rows = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(all_rows, mine, group=group)
-    spans = [(int(t[0]), int(t[1])) for t in all_rows]
+    if spans is None:
+        mine = torch.tensor([rows[0], rows[1]], dtype=torch.int64, device=local.device)
+        all_rows = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(all_rows, mine, group=group)
+        spans = [(int(t[0]), int(t[1])) for t in all_rows]
+    lead = tuple(local.shape[:-1])
     tallest = max(e - b for b, e in spans)
-    padded = torch.zeros((npairs, tallest * nbx), dtype=local.dtype, device=local.device)
-    padded[:, : local.shape[1]] = local
-    parts = [torch.zeros_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    full = torch.zeros((npairs, nby * nbx), dtype=local.dtype, device=local.device)
+    padded = torch.zeros(lead + (tallest * nbx,), dtype=local.dtype, device=local.device)
+    padded[..., : local.shape[-1]] = local
+    gathered = torch.empty((world,) + tuple(padded.shape), dtype=local.dtype, device=local.device)
+    # equal-sized views of one contiguous buffer: a single all_gather on NCCL and on gloo
+    dist.all_gather(list(gathered.unbind(0)), padded.contiguous(), group=group)
+    full = torch.zeros(lead + (nby * nbx,), dtype=local.dtype, device=local.device)
     covered = 0
-    for (b, e), part in zip(spans, parts):
-        full[:, b * nbx: e * nbx] = part[:, : (e - b) * nbx]
+    for r, (b, e) in enumerate(spans):
+        full[..., b * nbx: e * nbx] = gathered[r][..., : (e - b) * nbx]
         covered += e - b
     if covered != nby:
         raise RuntimeError("bands do not tile the frame: %r" % (spans,))
@@ -106,22 +115,19 @@ def gather_bands(local: "torch.Tensor", rows: Tuple[int, int], nby: int, nbx: in
 def search_banded(est, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, group=None, stream: int = 0,
                   balance: bool = True):
     """One frame (or batch) split by block-row bands over the ranks of `group`.
-    Every rank holds the full frames on its GPU, searches its band and gathers the
-    field.  Returns dict(mvx, mvy, ssd, score) of full (npairs, num_blocks) CUDA tensors."""
+    Every rank holds the full frames on its GPU, searches its band (the kernel writes the four
+    output arrays into one packed int32 tensor) and ONE all_gather completes the field.
+    Returns dict(mvx, mvy, ssd, score) of full (npairs, num_blocks) CUDA tensors."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     weights = row_costs(est.width, est.height, est.blk_dim, est.extra_span) if balance else None
-    b0, b1 = band_rows(est.blocks_y, world, rank, weights)
-    nb = est.num_blocks
-    dev = d_cur.device
-    out = {k: torch.zeros((npairs, nb), dtype=dt, device=dev)
-           for k, dt in (("mvx", torch.int32), ("mvy", torch.int32), ("ssd", torch.int32), ("score", torch.float32))}
-    est.search_device(d_cur, d_ref, pitch, pair_stride, npairs, out["mvx"], out["mvy"], out["ssd"], out["score"],
+    spans = all_band_rows(est.blocks_y, world, weights)
+    b0, b1 = spans[rank]
+    nb, nbx = est.num_blocks, est.blocks_x
+    packed = torch.zeros((4, npairs, nb), dtype=torch.int32, device=d_cur.device)  # mvx, mvy, ssd, score bits
+    est.search_device(d_cur, d_ref, pitch, pair_stride, npairs, packed[0], packed[1], packed[2], packed[3],
                       stream, b0, b1)
-    nbx = est.blocks_x
-    res = {}
-    for k, t in out.items():
-        res[k] = gather_bands(t[:, b0 * nbx: b1 * nbx].contiguous(), (b0, b1), est.blocks_y, nbx, group)
-    return res
+    full = gather_bands(packed[:, :, b0 * nbx: b1 * nbx], (b0, b1), est.blocks_y, nbx, group, spans)
+    return {"mvx": full[0], "mvy": full[1], "ssd": full[2], "score": full[3].view(torch.float32)}
