@@ -96,6 +96,7 @@ struct TiledParams {
   int s_bytes;            // FORM 2: tile bytes rounded up to 128
   int e_s;                // FORM 2: elements between the 4-aligned TMA origin and x0-R
   int s_y0;               // FORM 2: frame row of the table's first row
+  unsigned int inv_ndx;    // ceil(2^32 / (2R+1)): exact quotient by multiply-high for n < 2^16
   unsigned int *next_item; // global work counter of this launch (zeroed on the stream before it)
   Out out;
 };
@@ -288,10 +289,11 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       int task = c * 32 + lane;
       const bool active = task < I.ntasks;
       task = min(task, I.ntasks - 1);
-      const int part = task / I.tpp;
-      const int rem = task - part * I.tpp;
-      const int st = rem / ndx;
-      const int dx = rem - st * ndx;          // window-relative horizontal offset, mvx = dx - R
+      // task = (part * ns + strip) * ndx + dx; ndx divides by multiply-high (tasks < 2^16)
+      const int row = (int)__umulhi((unsigned)task, p.inv_ndx);  // = part * ns + strip
+      const int dx = task - row * ndx;        // window-relative horizontal offset, mvx = dx - R
+      const int part = row / I.ns;
+      const int st = row - part * I.ns;
       const int u = p.e + st * SW + dx;       // byte offset of the candidate column in a window row
       const uint32_t shift = 8u * (uint32_t)(u & 3);
       // vertical part: candidates [c0, c0 + L), evenly spread, the last one ends at nc
@@ -328,12 +330,13 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       if (FORM >= 1) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
-          uint32_t a = 0;
+          uint32_t a4[4] = {0u, 0u, 0u, 0u};  // four independent IDP chains instead of one long one
 #pragma unroll
           for (int r = 0; r < BH; r++)
 #pragma unroll
-            for (int w = 0; w < WPB; w++) a = __dp4a(cur[r][b * WPB + w], cur[r][b * WPB + w], a);
-          srun[b] = a;
+            for (int w = 0; w < WPB; w++)
+              a4[(r * WPB + w) & 3] = __dp4a(cur[r][b * WPB + w], cur[r][b * WPB + w], a4[(r * WPB + w) & 3]);
+          srun[b] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
 #pragma unroll
           for (int r = 0; r < BH; r++) qh[b][r] = 0u;
         }
@@ -744,6 +747,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.stages = (plan->max_smem - static_smem) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.out = o;
+  p.inv_ndx = (unsigned int)((0x100000000ull + (unsigned)(2 * g.R + 1) - 1) / (unsigned)(2 * g.R + 1));
   {
     const char *sk = getenv("ME_B200_SKEW");
     p.skew = sk ? atoi(sk) : 0;
