@@ -91,6 +91,7 @@ struct TiledParams {
   int stages;             // ring depth, 2..kMaxStages
   int parts_target;       // wanted vertical parts per column
   int e;                  // bytes between the 16-aligned TMA origin and the window origin x0-R
+  int skew;               // start-up stagger between the warps of one scheduler, in cycles
   int s_pitch, s_rows;    // FORM 2: energy tile, elements per row / rows (2R+1)
   int s_bytes;            // FORM 2: tile bytes rounded up to 128
   int e_s;                // FORM 2: elements between the 4-aligned TMA origin and x0-R
@@ -249,6 +250,14 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   __syncthreads();
   if (threadIdx.x < 32)
     for (int k = 0; k < p.stages; k++) refill(k);
+
+  // Optional start-up stagger of the warps that share a scheduler (env ME_B200_SKEW, cycles;
+  // default 0 = off).  Measured: no effect on throughput -- the warps drift apart by themselves.
+  if (p.skew > 0) {
+    const long long until = clock64() + (long long)(threadIdx.x >> 7) * p.skew;
+    while (clock64() < until) {
+    }
+  }
 
   // Every warp walks the ring; a stage that reported "no more work" is never re-armed and is
   // skipped from then on; the walk ends when all stages are dead.
@@ -738,6 +747,10 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.out = o;
   p.inv_ndx = (unsigned int)((0x100000000ull + (unsigned)(2 * g.R + 1) - 1) / (unsigned)(2 * g.R + 1));
+  {
+    const char *sk = getenv("ME_B200_SKEW");
+    p.skew = sk ? atoi(sk) : 0;
+  }
 
   EncodeTiledFn enc = get_encode();
   if (!enc) { *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
