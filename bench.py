@@ -402,7 +402,7 @@ def main():
             "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu_baseline:
-            cfps, cblocks, info = cpu_reference_rate(name, budget_s=15.0)
+            cfps, cblocks, info = cpu_reference_rate(name, budget_s=30.0, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": info["cores"],
                                     "kind": info["kind"], "sample": info["sample"], "blocks_per_s": cblocks}
         print(json.dumps(line), flush=True)
