@@ -724,7 +724,8 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       const double per_row = FORM == 1 ? (2.0 * WORDS + 8.0) : (2.0 * WORDS + 6.0);
       const double task = (double)L * BH * WORDS * (FORM >= 1 ? 1.0 : 2.0) + (double)(L + BH - 1) * per_row + 250.0;
       // warps flow from one item into the next, so chunks only quantise over the CTA's whole run
-      const double cost = (double)((per_cta * chunks + kWarps - 1) / kWarps) * task + 0.02 * per_cta * 2000.0;
+      // + per item: every warp's barrier wait / item decode / counter round trips, the re-arm and the publish
+      const double cost = (double)((per_cta * chunks + kWarps - 1) / kWarps) * task + 300.0 * per_cta;
       if (cost < best_cost * 0.999) { best_cost = cost; best_ns = ns; best_parts = parts; }
     }
   }
