@@ -23,15 +23,15 @@
 //       the candidate column by WORDS funnel shifts on the otherwise idle ALU pipe)
 //       is scored against all BH current rows, feeding BH live candidates whose
 //       accumulators rotate through a register file of BH slots (the period-BH
-//       loop is fully unrolled so every index is static).  Two exact integer
-//       formulations of the SSD are compiled (template FORM):
-//         FORM 1 (default)  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref: one IDP.4A.U8.U8
+//       loop is fully unrolled so every index is static).  Three exact integer
+//       formulations of the SSD are compiled (template FORM; 2 is the default):
+//         FORM 1  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref: one IDP.4A.U8.U8
 //                per 4 pixels for the cross term; sum ref^2 over the candidate's rows is a
 //                sliding sum of per-row IDP.4A(ref,ref), sum cur^2 is per task.  Half the
 //                instructions of FORM 0 (the unrolled loop fits the instruction cache),
 //                FMA-pipe bound, and zero-padded current rows/columns make partial edge
 //                blocks free (their reference pixels are masked out of sum ref^2).
-//         FORM 2  as FORM 1, but sum ref^2 of every candidate position comes from a table that a
+//         FORM 2 (default)  as FORM 1, but sum ref^2 of every candidate position comes from a table that a
 //                small pre-pass kernel (box_energy_kernel) builds per reference frame; the tile of
 //                the table that belongs to an item rides in the stage next to the window (third
 //                TMA load), so a finished candidate costs one LDS instead of 4 IDP.4A per row
@@ -47,7 +47,8 @@
 //       (main.c:53-62); ssd < 2^24 makes float(ssd)/float(w*h) the reference's
 //       score bit for bit (main.c:19-27).
 //     * the last warp to leave an item writes the item's motion vectors / SSD /
-//       score (SoA) and re-arms the stage with the TMA of the item `stages` ahead.
+//       score (SoA), takes the next item from a launch-wide atomic counter (dynamic
+//       scheduling over all CTAs) and re-arms the stage with its TMA loads.
 //   Vertical parts always hold m*BH + 1 candidates, so the ramp-up and ramp-down
 //   of the rotating accumulators have a static shape and are skipped with
 //   warp-uniform branches: no wasted pixel-compares, no validity tests in the loop.
