@@ -43,11 +43,12 @@ extern "C" {
 #define ME_ERR_STATE       -6 /* wait on an idle slot, submit on a busy one                    */
 
 /* kernel selection (me_b200_create_ex).  AUTO picks the tuned kernel when the
- * geometry allows it and the generic exact kernel otherwise; both give
- * identical results. */
+ * geometry allows it (the small-span kernel for R <= 4) and the generic exact kernel otherwise;
+ * all give identical results. */
 #define ME_KERNEL_AUTO    0
 #define ME_KERNEL_GENERIC 1
 #define ME_KERNEL_TILED   2
+#define ME_KERNEL_DIRECT  3 /* small spans (R <= 4): one thread per (block, candidate) */
 
 #define ME_B200_MAX_SLOTS 4
 
@@ -74,7 +75,7 @@ void me_b200_destroy(me_b200_ctx *ctx);
 int      me_b200_num_blocks(const me_b200_ctx *ctx);   /* prediction_frame.c:9-12 */
 int      me_b200_blocks_x(const me_b200_ctx *ctx);
 int      me_b200_blocks_y(const me_b200_ctx *ctx);
-int      me_b200_kernel_in_use(const me_b200_ctx *ctx); /* ME_KERNEL_GENERIC or _TILED */
+int      me_b200_kernel_in_use(const me_b200_ctx *ctx); /* ME_KERNEL_GENERIC, _TILED or _DIRECT */
 /* exact work counts of one frame pair */
 uint64_t me_b200_pixel_compares(const me_b200_ctx *ctx);
 uint64_t me_b200_candidates(const me_b200_ctx *ctx);

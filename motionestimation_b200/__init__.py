@@ -13,7 +13,7 @@ souravBhat/MotionEstimation.
 """
 from .lib import (  # noqa: F401
     ME_OK, ME_ERR_INVALID_ARG, ME_ERR_UNSUPPORTED, ME_ERR_CUDA, ME_ERR_NO_DEVICE,
-    ME_ERR_NOMEM, ME_ERR_STATE, ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED,
+    ME_ERR_NOMEM, ME_ERR_STATE, ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT,
     MeError, Block, PredictionFrame, load_library, library_path, device_count,
     Estimator, create_prediction_frame, search_prediction_frame, int_peak, PEAK_NAMES,
 )

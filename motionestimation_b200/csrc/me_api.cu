@@ -77,6 +77,18 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
   g.by_begin = by_begin;
   g.by_count = by_end - by_begin;
   if (g.by_count <= 0 || npairs <= 0) return ME_OK;
+  // small spans: one thread per (block, candidate)
+  const bool direct_ok = me::direct_supported(g, f.pitch, f.pair_stride, f.cur, f.ref);
+  if (ctx->kernel_req == ME_KERNEL_DIRECT && !direct_ok) {
+    snprintf(ctx->err, 256, "small-span kernel requested but geometry/layout unsupported");
+    return ME_ERR_UNSUPPORTED;
+  }
+  if (direct_ok && (ctx->kernel_req == ME_KERNEL_AUTO || ctx->kernel_req == ME_KERNEL_DIRECT)) {
+    cudaError_t e = me::launch_direct(g, f, npairs, o, s);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_direct");
+    ctx->launches += (uint64_t)((npairs + 65534) / 65535);
+    return ME_OK;
+  }
   bool tiled = ctx->kernel_req != ME_KERNEL_GENERIC && ctx->plan &&
                me::tiled_supported(g, f.pitch, f.pair_stride, f.cur, f.ref);
   if (ctx->kernel_req == ME_KERNEL_TILED && !tiled) {
@@ -162,7 +174,8 @@ int me_b200_create_ex(me_b200_ctx **out, int device, int width, int height, int 
   if (!out) return ME_ERR_INVALID_ARG;
   *out = nullptr;
   if (width <= 0 || height <= 0 || blk_dim <= 0 || extra_span < 0 || max_pairs < 1) return ME_ERR_INVALID_ARG;
-  if (kernel != ME_KERNEL_AUTO && kernel != ME_KERNEL_GENERIC && kernel != ME_KERNEL_TILED)
+  if (kernel != ME_KERNEL_AUTO && kernel != ME_KERNEL_GENERIC && kernel != ME_KERNEL_TILED &&
+      kernel != ME_KERNEL_DIRECT)
     return ME_ERR_INVALID_ARG;
   if (blk_dim > 256 || extra_span > 1024) return ME_ERR_UNSUPPORTED;
   if ((long long)width * height > (1ll << 30)) return ME_ERR_UNSUPPORTED;
@@ -215,7 +228,7 @@ int me_b200_create_ex(me_b200_ctx **out, int device, int width, int height, int 
       check(cudaMemsetAsync(s.d_ref, 0, fb, s.stream), "memset");
     }
   }
-  if (rc == ME_OK && kernel != ME_KERNEL_GENERIC) {
+  if (rc == ME_OK && kernel != ME_KERNEL_GENERIC && kernel != ME_KERNEL_DIRECT) {
     cudaError_t pe = me::tiled_plan_create(&ctx->plan, ctx->g, max_pairs);
     if (pe != cudaSuccess) {
       ctx->plan = nullptr;
@@ -231,6 +244,13 @@ int me_b200_create_ex(me_b200_ctx **out, int device, int width, int height, int 
     ctx->kernel = (ctx->plan && me::tiled_supported(ctx->g, f.pitch, f.pair_stride, f.cur, f.ref))
                       ? ME_KERNEL_TILED
                       : ME_KERNEL_GENERIC;
+    if ((kernel == ME_KERNEL_AUTO || kernel == ME_KERNEL_DIRECT) &&
+        me::direct_supported(ctx->g, f.pitch, f.pair_stride, f.cur, f.ref))
+      ctx->kernel = ME_KERNEL_DIRECT;
+    if (kernel == ME_KERNEL_DIRECT && ctx->kernel != ME_KERNEL_DIRECT) {
+      snprintf(g_err, 256, "small-span kernel does not support B=%d R=%d", blk_dim, extra_span);
+      rc = ME_ERR_UNSUPPORTED;
+    }
     if (kernel == ME_KERNEL_TILED && ctx->kernel != ME_KERNEL_TILED) {
       snprintf(g_err, 256, "tiled kernel does not support B=%d R=%d", blk_dim, extra_span);
       rc = ME_ERR_UNSUPPORTED;

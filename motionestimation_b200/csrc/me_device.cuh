@@ -33,6 +33,10 @@ struct Frames {
 // host-side launchers (defined in the .cu files)
 cudaError_t launch_generic(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s);
 
+// Small-span kernel (R <= 4): one thread per (block, candidate); the memory-bound end of the path.
+bool direct_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref);
+cudaError_t launch_direct(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s);
+
 // Tiled kernel: returns false from tiled_supported() when the geometry is not
 // one it is specialised for (the caller then uses the generic kernel).
 bool tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref);

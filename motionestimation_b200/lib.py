@@ -23,7 +23,7 @@ ME_ERR_CUDA = -3
 ME_ERR_NO_DEVICE = -4
 ME_ERR_NOMEM = -5
 ME_ERR_STATE = -6
-ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED = 0, 1, 2
+ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT = 0, 1, 2, 3
 ME_B200_MAX_SLOTS = 4
 
 PEAK_NAMES = ["IDP4A", "VABSDIFF4", "SSD_PAIR", "IADD3", "LOP3", "IMAD", "VIMNMX",

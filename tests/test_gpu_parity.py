@@ -56,7 +56,39 @@ RANDOM_GEOMS = [
     # spans that are not multiples of 4 / 16 (TMA origin phases), odd block counts, half-height bottom rows
     (16, 7, 96, 64), (8, 5, 64, 48), (16, 33, 128, 104), (8, 13, 88, 60), (16, 1, 48, 40), (8, 2, 24, 20),
     (16, 120, 64, 48), (16, 121, 64, 48), (8, 64, 96, 72), (16, 9, 336, 24),
+    # small spans (R <= 4 runs the one-thread-per-candidate kernel), partial right/bottom blocks
+    (16, 4, 80, 64), (16, 2, 100, 50), (8, 3, 70, 45), (16, 0, 64, 64), (8, 1, 16, 8), (16, 3, 300, 70),
+    (8, 4, 136, 40),
 ]
+
+
+@pytest.mark.parametrize("kernel", [me.ME_KERNEL_DIRECT, me.ME_KERNEL_TILED], ids=["direct", "tiled"])
+@pytest.mark.parametrize("B,R,W,H", [g for g in RANDOM_GEOMS if g[0] in (8, 16) and g[1] <= 4])
+def test_small_span_kernels(orc, B, R, W, H, kernel):
+    """Small spans: both the dedicated small-span kernel and the tuned kernel (forced) are exact."""
+    if kernel == me.ME_KERNEL_TILED and (W < B or H < B):
+        pytest.skip("tuned kernel needs at least one full block")
+    test_random_differential(orc, B, R, W, H, kernel)
+
+
+def test_small_span_full_size(orc):
+    """1080p, 16x16, +-2 (memory-bound case): the small-span kernel is what AUTO runs; equals the
+    oracle on the first/last block rows and recovers a pure translation everywhere."""
+    W, H, B, R = 1920, 1080, 16, 2
+    rng = np.random.Generator(np.random.PCG64(3))
+    base = rng.integers(0, 256, (H + 8, W + 8), dtype=np.uint8)
+    ref = np.ascontiguousarray(base[4:4 + H, 4:4 + W])
+    cur = np.ascontiguousarray(base[4 - 1:4 - 1 + H, 4 + 2:4 + 2 + W])   # cur(x,y) = ref(x+2, y-1)
+    cur2, ref2 = me.tiled_frames(W, H)
+    with me.Estimator(W, H, B, R, max_pairs=2) as est:
+        assert est.kernel_in_use == me.ME_KERNEL_DIRECT
+        out = est.search_u8(np.stack([cur, cur2]), np.stack([ref, ref2]))
+    x0, y0, w, h = me.block_grid(W, H, B)
+    interior = (x0 + 2 >= 0) & (y0 - 1 >= 0) & (x0 + w + 2 <= W) & (y0 + h - 1 <= H)
+    assert np.all(out["mvx"][0][interior] == 2) and np.all(out["mvy"][0][interior] == -1)
+    assert not out["ssd"][0][interior].any()
+    o = orc.search(cur2, ref2, B, R)
+    check_against(out, 1, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), "tiled foreman +-2")
 
 
 # tuned-kernel formulations (env ME_B200_FORM, read when the context is created): default = energy
