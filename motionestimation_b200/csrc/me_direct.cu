@@ -7,7 +7,7 @@
 // this kernel maps one thread to one (block, candidate) pair instead:
 //   * a CTA owns a 128 x 32 pixel tile of blocks (8 x 2 blocks of 16x16 or 16 x 4 blocks of 8x8);
 //     the current tile and the reference tile + R halo are staged in shared memory once with
-//     coalesced 32-bit loads (each frame byte is read from HBM ~1.1 times);
+//     coalesced 16-byte loads (each frame byte is read from HBM ~1.1 times);
 //   * a thread scores candidates idx = tid, tid + 256, ... of the tile: per row, the aligned
 //     reference words around the candidate column are funnel-shifted into place and compared with
 //     VABSDIFF4.U8 + IDP.4A.U8.U8 (exact integer SSD);
@@ -22,7 +22,7 @@ namespace {
 
 constexpr int kTX = 128, kTY = 32;  // tile of pixels per CTA
 constexpr int kMaxR = 4;
-constexpr int kRefPitch = kTX + 16;                 // >= kTX + 2R + 3, multiple of 4
+constexpr int kRefPitch = kTX + 32;                 // >= 15 + kTX + 2R + 3, multiple of 16
 constexpr int kRefRows = kTY + 2 * kMaxR;
 constexpr int kThreads = 256;
 
@@ -41,31 +41,29 @@ direct_search_kernel(Geom g, Frames f, Out o) {
   const uint8_t *cur = f.cur + (size_t)blockIdx.z * f.pair_stride;
   const uint8_t *ref = f.ref + (size_t)blockIdx.z * f.pair_stride;
 
-  // stage the current tile and the reference tile + halo (zeros outside the frame)
-  for (int i = threadIdx.x; i < kTY * (kTX / 4); i += kThreads) {
-    const int r = i / (kTX / 4), k = i - r * (kTX / 4);
-    const int y = ty0 + r, x = tx0 + 4 * k;
-    uint32_t w = 0;
-    if (y < g.H && x < g.W) {
-      const uint8_t *q = cur + (size_t)y * f.pitch + x;
-      if (x + 4 <= g.W) w = *reinterpret_cast<const uint32_t *>(q);
-      else for (int b = 0; b < 4; b++) if (x + b < g.W) w |= (uint32_t)q[b] << (8 * b);
-    }
-    reinterpret_cast<uint32_t *>(s_cur)[i] = w;
+  // stage the current tile and the reference tile + halo (zeros outside the frame); 16-byte loads
+  // wherever the 16 bytes lie inside the frame and the layout is 16-byte aligned
+  const bool vec = ((f.pitch & 15) == 0) && ((((uintptr_t)cur | (uintptr_t)ref) & 15) == 0);
+  auto load16 = [&](const uint8_t *base, int x, int y) -> uint4 {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y < 0 || y >= g.H || x + 15 < 0 || x >= g.W) return v;
+    const uint8_t *q = base + (size_t)y * f.pitch;
+    if (vec && x >= 0 && x + 16 <= g.W) return *reinterpret_cast<const uint4 *>(q + x);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int b = 0; b < 16; b++)
+      if (x + b >= 0 && x + b < g.W) w[b >> 2] |= (uint32_t)q[x + b] << (8 * (b & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  for (int i = threadIdx.x; i < kTY * (kTX / 16); i += kThreads) {
+    const int r = i / (kTX / 16), k = i - r * (kTX / 16);
+    reinterpret_cast<uint4 *>(s_cur)[i] = load16(cur, tx0 + 16 * k, ty0 + r);
   }
-  // reference columns start at the 4-aligned column left of tx0 - R
-  const int rx0 = (tx0 - R) & ~3;  // may be negative
-  const int ex = tx0 - R - rx0;    // 0..3 bytes between the aligned origin and tx0 - R
-  for (int i = threadIdx.x; i < (kTY + 2 * R) * (kRefPitch / 4); i += kThreads) {
-    const int r = i / (kRefPitch / 4), k = i - r * (kRefPitch / 4);
-    const int y = ty0 - R + r, x = rx0 + 4 * k;
-    uint32_t w = 0;
-    if (y >= 0 && y < g.H && x + 3 >= 0 && x < g.W) {
-      const uint8_t *q = ref + (size_t)y * f.pitch;
-      if (x >= 0 && x + 4 <= g.W) w = *reinterpret_cast<const uint32_t *>(q + x);
-      else for (int b = 0; b < 4; b++) if (x + b >= 0 && x + b < g.W) w |= (uint32_t)q[x + b] << (8 * b);
-    }
-    reinterpret_cast<uint32_t *>(s_ref)[r * (kRefPitch / 4) + k] = w;
+  // reference columns start at the 16-aligned column left of tx0 - R
+  const int rx0 = (tx0 - R) & ~15;  // may be negative
+  const int ex = tx0 - R - rx0;     // 0..15 bytes between the aligned origin and tx0 - R
+  for (int i = threadIdx.x; i < (kTY + 2 * R) * (kRefPitch / 16); i += kThreads) {
+    const int r = i / (kRefPitch / 16), k = i - r * (kRefPitch / 16);
+    reinterpret_cast<uint4 *>(s_ref)[r * (kRefPitch / 16) + k] = load16(ref, rx0 + 16 * k, ty0 - R + r);
   }
   if (threadIdx.x < NBLK) s_best[threadIdx.x] = 0xffffffffu;
   __syncthreads();
