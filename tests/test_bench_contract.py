@@ -1,0 +1,55 @@
+"""bench.py keeps the driver's JSON contract: the reference arm on CPU, the B200 arm on a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def run_bench(*args):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    """--impl reference: the reference's own CPU implementation (oracle/_ref when built, else the
+    oracle port), same metric/unit/config keys, no GPU work."""
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "foreman_8x8_pm12")
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"] == "foreman_8x8_pm12" and d["dtype"] == "u8"
+    assert d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+
+
+def test_reference_arm_other_ranks_are_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_b200_arm_line():
+    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", "4", "--no-cpu-baseline")
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["metric"] == "1080p_frames_per_sec_full_search_pm32" and d["unit"] == "frames/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["scaling"] == "weak"
+    assert d["config"]["workload"] == "1080p_16x16_pm32" and d["config"]["kernel"] == "tiled"
+    assert d["value"] > 1000 and d["gpu_launches"] >= 2
+    r = d["roofline"]
+    assert r["bound"] == "int_alu" and 0.3 < r["frac"] < 1.1 and r["peak"] > 30 and r["unit"] == "T lane-instr/s"
+    e = d["e2e"]
+    assert e["value"] > 500 and e["h2d_bytes_per_step"] == 2 * 4 * 1920 * 1080 and e["d2h_bytes_per_step"] > 0
+    assert "clocks" in d and "reasons" in d["clocks"]
