@@ -285,6 +285,19 @@ def test_sequence_shares_frames(orc, B, R, max_pairs):
         check_against(out, i, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {i}")
 
 
+def test_batches_larger_than_the_context(orc):
+    """me_b200_search_u8 with more pairs than max_pairs: chunked over the slots, same results."""
+    W, H, B, R = 176, 144, 16, 16
+    pairs = [me.shifted_noise_pair(W, H, seed=s, shift=(s % 5 - 2, 1 - s % 3)) for s in range(11)]
+    cur = np.stack([p[0] for p in pairs])
+    ref = np.stack([p[1] for p in pairs])
+    with me.Estimator(W, H, B, R, max_pairs=2) as est:
+        out = est.search_u8(cur, ref)
+    for i, (c, r) in enumerate(pairs):
+        o = orc.search(c, r, B, R)
+        check_against(out, i, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {i}")
+
+
 def recompute_ssd(cur, ref, B, mvx, mvy):
     """SSD of the chosen candidates from the frames alone (numpy)."""
     H, W = cur.shape
