@@ -50,6 +50,19 @@ extern "C" {
 #define ME_KERNEL_TILED   2
 #define ME_KERNEL_DIRECT  3 /* small spans (R <= 4): one thread per (block, candidate) */
 
+/* matching cost (me_b200_set_cost).  MSE: src/cpu/main.c:18-36.  SSIM: src/common/ssim.c:44-60,
+ * maximised, as src/cpu/main_ssim.c runs it. */
+#define ME_COST_MSE  0
+#define ME_COST_SSIM 1
+
+/* search pattern (me_b200_set_search).  FULL is the reference's exhaustive scan.  THREE_STEP and
+ * DIAMOND are NOT in the reference (BASELINE.json config 4 names them): they are defined in
+ * DESIGN.md section 5.6 / csrc/me_fast.cu on top of the reference's window (main.c:69-76), cost
+ * (main.c:18-27) and tie rule (main.c:56) -- parity unpinned. */
+#define ME_SEARCH_FULL       0
+#define ME_SEARCH_THREE_STEP 1
+#define ME_SEARCH_DIAMOND    2
+
 #define ME_B200_MAX_SLOTS 4
 
 typedef struct me_b200_ctx me_b200_ctx;
@@ -82,6 +95,20 @@ uint64_t me_b200_candidates(const me_b200_ctx *ctx);
 /* kernel launches issued by this context so far (search + pack kernels) */
 uint64_t me_b200_launch_count(const me_b200_ctx *ctx);
 
+/* ---- mode of a context (default: ME_COST_MSE, ME_SEARCH_FULL) ---------------------------
+ * Every search entry point below that takes a ctx (search_u8, submit/wait, sequences, device,
+ * band) then runs that cost / pattern with the same argument meaning.  With ME_COST_SSIM
+ *   score[] = the float findBestBlkSSIM returns (main_ssim.c:29; 0 when no candidate scored > 0)
+ *   ssd[]   = 1 when some candidate scored above 0, else 0.  In that case the reference leaves
+ *             the motion vector uninitialised (ssim.c:88-103, main_ssim.c:26-27); here it is (0,0).
+ * SSIM with a fast pattern is not defined (ME_ERR_UNSUPPORTED). */
+int me_b200_set_cost(me_b200_ctx *ctx, int cost);
+int me_b200_set_search(me_b200_ctx *ctx, int search);
+/* candidate evaluations of all fast searches this context has run so far (synchronises). */
+int me_b200_fast_evaluations(me_b200_ctx *ctx, uint64_t *evaluations);
+/* first step of the three-step pattern: largest power of two <= max(1, (extra_span+1)/2). */
+int me_b200_tss_first_step(int extra_span);
+
 /* ---- reference drop-in ---------------------------------------------------------
  * replaces: the whole dispatch loop main.c:144-158, i.e. one call instead of
  * num_blks x thpool_add_work(runFindBestBlkMse).  pf->frame is the current
@@ -96,6 +123,14 @@ uint64_t me_b200_launch_count(const me_b200_ctx *ctx);
 int me_b200_search(predictionFrame *pf, const int *refFrame, int extraSpan);
 int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpan,
                           float *scores, uint32_t *ssd);
+/* SSIM twin -- replaces the sequential loop src/cpu/main_ssim.c:67-77 over findBestBlkSSIM
+ * (main_ssim.c:16-30 -> ssim.c:83-107).  scores[i] = best SSIM, found[i] as ssd[] above. */
+int me_b200_search_ssim(predictionFrame *pf, const int *refFrame, int extraSpan);
+int me_b200_search_ssim_scores(predictionFrame *pf, const int *refFrame, int extraSpan,
+                               float *scores, uint32_t *found);
+/* fast-search twin on the reference's structs; search = ME_SEARCH_THREE_STEP / _DIAMOND. */
+int me_b200_search_fast(predictionFrame *pf, const int *refFrame, int extraSpan, int search,
+                        float *scores, uint32_t *ssd);
 /* frees the cached implicit contexts (optional; also done at process exit). */
 void me_b200_release_cached(void);
 

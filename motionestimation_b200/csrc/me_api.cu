@@ -32,6 +32,9 @@ struct me_b200_ctx {
   me_slot slots[ME_B200_MAX_SLOTS];
   me::TiledPlan *plan = nullptr;
   uint64_t launches = 0;
+  int cost = ME_COST_MSE;          // me_b200_set_cost
+  int search = ME_SEARCH_FULL;     // me_b200_set_search
+  unsigned long long *d_evals = nullptr;  // fast search: candidate evaluations so far
   char err[256] = {0};
   // scratch for the int-frame drop-in path
   uint8_t *h_cur = nullptr, *h_ref = nullptr;  // pinned, W*H each
@@ -77,6 +80,25 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
   g.by_begin = by_begin;
   g.by_count = by_end - by_begin;
   if (g.by_count <= 0 || npairs <= 0) return ME_OK;
+  if (ctx->search != ME_SEARCH_FULL) {
+    // three-step / diamond search (MSE cost), one warp per block
+    cudaError_t e = me::launch_fast(g, f, npairs, o, ctx->search, ctx->d_evals, s);
+    if (e == cudaErrorInvalidConfiguration) {
+      (void)cudaGetLastError();
+      snprintf(ctx->err, 256, "fast search: block size %d does not fit shared memory", g.B);
+      return ME_ERR_UNSUPPORTED;
+    }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_fast");
+    ctx->launches += (uint64_t)((npairs + 65534) / 65535);
+    return ME_OK;
+  }
+  if (ctx->cost == ME_COST_SSIM) {
+    unsigned long long n = 0;
+    cudaError_t e = me::launch_ssim(g, f, npairs, o, ctx->kernel_req != ME_KERNEL_GENERIC, s, &n);
+    ctx->launches += n;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_ssim");
+    return ME_OK;
+  }
   // small spans: one thread per (block, candidate)
   const bool direct_ok = me::direct_supported(g, f.pitch, f.pair_stride, f.cur, f.ref);
   if (ctx->kernel_req == ME_KERNEL_DIRECT && !direct_ok) {
@@ -280,6 +302,7 @@ void me_b200_destroy(me_b200_ctx *ctx) {
       if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->plan) me::tiled_plan_destroy(ctx->plan);
+    cudaFree(ctx->d_evals);
     cudaFreeHost(ctx->h_cur);
     cudaFreeHost(ctx->h_ref);
     cudaFreeHost(ctx->h_mvx);
@@ -306,6 +329,42 @@ uint64_t me_b200_candidates(const me_b200_ctx *ctx) {
 uint64_t me_b200_launch_count(const me_b200_ctx *ctx) {
   return ctx ? ctx->launches + me::tiled_plan_launches(ctx->plan) : 0;
 }
+
+int me_b200_set_cost(me_b200_ctx *ctx, int cost) {
+  if (!ctx || (cost != ME_COST_MSE && cost != ME_COST_SSIM)) return ME_ERR_INVALID_ARG;
+  if (cost == ME_COST_SSIM && ctx->search != ME_SEARCH_FULL) return ME_ERR_UNSUPPORTED;
+  ctx->cost = cost;
+  return ME_OK;
+}
+
+int me_b200_set_search(me_b200_ctx *ctx, int search) {
+  if (!ctx || (search != ME_SEARCH_FULL && search != ME_SEARCH_THREE_STEP && search != ME_SEARCH_DIAMOND))
+    return ME_ERR_INVALID_ARG;
+  if (search != ME_SEARCH_FULL && ctx->cost != ME_COST_MSE) return ME_ERR_UNSUPPORTED;
+  if (search != ME_SEARCH_FULL && !ctx->d_evals) {
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    ME_CUDA(ctx, cudaMalloc((void **)&ctx->d_evals, 256));
+    ME_CUDA(ctx, cudaMemset(ctx->d_evals, 0, 256));
+  }
+  ctx->search = search;
+  return ME_OK;
+}
+
+int me_b200_fast_evaluations(me_b200_ctx *ctx, uint64_t *evaluations) {
+  if (!ctx || !evaluations) return ME_ERR_INVALID_ARG;
+  *evaluations = 0;
+  if (!ctx->d_evals) return ME_OK;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  ME_CUDA(ctx, cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  ME_CUDA(ctx, cudaMemcpy(&v, ctx->d_evals, sizeof v, cudaMemcpyDeviceToHost));
+  *evaluations = v;
+  return ME_OK;
+}
+
+int me_b200_tss_first_step(int extra_span) { return me::tss_first_step(extra_span); }
 
 void *me_b200_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -496,7 +555,7 @@ int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
 
 namespace {
 struct cached_ctx {
-  int device, W, H, B, R;
+  int device, W, H, B, R, cost, search;
   me_b200_ctx *ctx;
 };
 std::mutex g_cache_mu;
@@ -528,8 +587,9 @@ void me_b200_release_cached(void) {
   g_cache_n = 0;
 }
 
-int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpan, float *scores,
-                          uint32_t *ssd) {
+namespace {
+int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int cost, int search, float *scores,
+                  uint32_t *ssd) {
   if (!pf || !pf->frame || !pf->blks || !refFrame) return ME_ERR_INVALID_ARG;
   if (pf->width <= 0 || pf->height <= 0 || pf->blk_dim <= 0 || extraSpan < 0) return ME_ERR_INVALID_ARG;
   const int W = pf->width, H = pf->height, B = pf->blk_dim;
@@ -548,17 +608,23 @@ int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpa
   me_b200_ctx *ctx = nullptr;
   for (int i = 0; i < g_cache_n; i++)
     if (g_cache[i].device == device && g_cache[i].W == W && g_cache[i].H == H && g_cache[i].B == B &&
-        g_cache[i].R == extraSpan)
+        g_cache[i].R == extraSpan && g_cache[i].cost == cost && g_cache[i].search == search)
       ctx = g_cache[i].ctx;
   if (!ctx) {
     int rc = me_b200_create_ex(&ctx, device, W, H, B, extraSpan, 1, ME_KERNEL_AUTO);
     if (rc) return rc;
+    rc = me_b200_set_cost(ctx, cost);
+    if (rc == ME_OK) rc = me_b200_set_search(ctx, search);
+    if (rc) {
+      me_b200_destroy(ctx);
+      return rc;
+    }
     if (g_cache_n == 8) {
       me_b200_destroy(g_cache[0].ctx);
       memmove(&g_cache[0], &g_cache[1], sizeof(cached_ctx) * 7);
       g_cache_n = 7;
     }
-    g_cache[g_cache_n++] = cached_ctx{device, W, H, B, extraSpan, ctx};
+    g_cache[g_cache_n++] = cached_ctx{device, W, H, B, extraSpan, cost, search, ctx};
     if (!g_atexit) {
       g_atexit = true;
       atexit(me_b200_release_cached);
@@ -590,9 +656,30 @@ int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpa
   if (ssd) memcpy(ssd, ctx->h_ssd, nb * 4);
   return ME_OK;
 }
+}  // namespace
+
+int me_b200_search_scores(predictionFrame *pf, const int *refFrame, int extraSpan, float *scores,
+                          uint32_t *ssd) {
+  return dropin_search(pf, refFrame, extraSpan, ME_COST_MSE, ME_SEARCH_FULL, scores, ssd);
+}
 
 int me_b200_search(predictionFrame *pf, const int *refFrame, int extraSpan) {
-  return me_b200_search_scores(pf, refFrame, extraSpan, nullptr, nullptr);
+  return dropin_search(pf, refFrame, extraSpan, ME_COST_MSE, ME_SEARCH_FULL, nullptr, nullptr);
+}
+
+int me_b200_search_ssim_scores(predictionFrame *pf, const int *refFrame, int extraSpan, float *scores,
+                               uint32_t *found) {
+  return dropin_search(pf, refFrame, extraSpan, ME_COST_SSIM, ME_SEARCH_FULL, scores, found);
+}
+
+int me_b200_search_ssim(predictionFrame *pf, const int *refFrame, int extraSpan) {
+  return dropin_search(pf, refFrame, extraSpan, ME_COST_SSIM, ME_SEARCH_FULL, nullptr, nullptr);
+}
+
+int me_b200_search_fast(predictionFrame *pf, const int *refFrame, int extraSpan, int search, float *scores,
+                        uint32_t *ssd) {
+  if (search != ME_SEARCH_THREE_STEP && search != ME_SEARCH_DIAMOND) return ME_ERR_INVALID_ARG;
+  return dropin_search(pf, refFrame, extraSpan, ME_COST_MSE, search, scores, ssd);
 }
 
 }  // extern "C"

@@ -47,6 +47,18 @@ unsigned long long tiled_plan_launches(const TiledPlan *plan);  // kernels launc
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err_text);
 
+// SSIM-cost full search (me_ssim.cu; reference: src/cpu/main_ssim.c + src/common/ssim.c).
+// Out.score = best SSIM, Out.ssd = 1 when some candidate scored above 0 (else MV = (0,0)).
+bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur);
+cudaError_t launch_ssim(const Geom &g, const Frames &f, int npairs, const Out &o, bool tiled, cudaStream_t s,
+                        unsigned long long *launches);
+
+// Fast searches (me_fast.cu; absent from the reference, defined in that file's header).
+// algo 1 = three-step, 2 = diamond; evals = optional device counter of candidate evaluations.
+int tss_first_step(int R);
+cudaError_t launch_fast(const Geom &g, const Frames &f, int npairs, const Out &o, int algo,
+                        unsigned long long *evals, cudaStream_t s);
+
 cudaError_t launch_postprocess(const Geom &g, const uint8_t *cur, const uint8_t *ref, size_t pitch,
                                const int32_t *mvx, const int32_t *mvy, uint8_t *out5,
                                unsigned long long *sq_err, uint32_t *mx, cudaStream_t s);

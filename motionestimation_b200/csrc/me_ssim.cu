@@ -1,0 +1,548 @@
+// me_ssim.cu -- SSIM-cost full search for sm_100a.
+//
+// Reference being replaced: the sequential loop src/cpu/main_ssim.c:67-77 over
+// findBestBlkSSIM (main_ssim.c:16-30) -> findBestMatchSSIM (src/common/ssim.c:83-107)
+// -> computeSSIM (ssim.c:44-60) with computeMean / computeVar / computeCrossVar
+// (ssim.c:3-41).  Results are bit-identical: same motion vectors, same float score bits.
+//
+// How a float cost can be reproduced bit for bit on a GPU:
+//   * every operation that rounds is issued as an explicit round-to-nearest intrinsic
+//     (__fadd_rn, __fmul_rn, __fdiv_rn, __fsqrt_rn): nothing is contracted into an FMA and
+//     nothing is reordered; the reference build (gcc, x86-64, no FMA) rounds after every
+//     float operation as well.  sqrt() through double and back (ssim.c:52-53) equals the
+//     correctly rounded float sqrt.
+//   * the variance (ssim.c:16-27) is a float sum of rounded squares: it IS order dependent and
+//     is accumulated in the reference's raster order, one thread per rectangle.
+//   * the mean's pixel sum (ssim.c:3-14) and -- because computeCrossVar receives the two means
+//     truncated to int (ssim.h:12) -- the cross sum (ssim.c:29-41) are sums of integers whose
+//     partial sums stay below 2^24 (w*h <= 65793, resp. w*h <= 258): exact in float, hence
+//     computed in integer arithmetic in any order.  The cross sum becomes
+//         sum r*c - imr*sum c - imc*sum r + n*imr*imc,
+//     so the only per-pixel work of a candidate is the dot product sum r*c: one IDP.4A.U8.U8
+//     per 4 pixels, the same instruction stream as the MSE search's cross term.
+//   * mean and standard deviation of the reference rectangle depend on the POSITION only, not
+//     on the block that looks at it (the reference recomputes them (2R+1)^2/B^2 times): a
+//     pre-pass tabulates them per reference frame (ssim_stats_kernel).
+//   * the winner is the first strict maximum above 0 in y-major/x-minor order (ssim.c:98-106):
+//     for positive floats the bit pattern is monotone, so the unsigned maximum of
+//     (score bits << 32 | ~visit index) is exactly that candidate.
+//   * when no candidate scores above 0 the reference never writes the motion vector
+//     (uninitialised heap, ssim.c:88-103): reported here as MV (0,0), score 0, found = 0.
+//
+// Kernels
+//   ssim_generic_kernel   any geometry: one CTA per block, every statistic on the fly, literal
+//                         float cross sum once w*h > 258.  Parity safety net + partial edge blocks.
+//   ssim_stats_kernel<B>  pre-pass: {mean, stddev} of every BxB rectangle of the reference frame.
+//   ssim_tiled_kernel<..> 8x8 / 16x16 full blocks: a CTA owns GX adjacent blocks of one block row,
+//                         stages their common window once; a thread streams down a window column
+//                         and scores VB vertically adjacent candidates per pass (each loaded row
+//                         feeds up to VB dot products); float epilogue per candidate.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "me_device.cuh"
+
+namespace me {
+
+namespace {
+
+// ssim.c:47 -- double literals narrowed to float by the declaration
+__device__ __forceinline__ float kC1() { return (float)0.01; }
+__device__ __forceinline__ float kC2() { return (float)0.09; }
+__device__ __forceinline__ float kC3() { return (float)0.045; }
+
+// ssim.c:55-58 from the statistics of the two rectangles and the cross term (ssim.c:54)
+__device__ __forceinline__ float ssim_from_stats(float mr, float sr, float mc, float sc, float cross) {
+  const float lum = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.0f, mr), mc), kC1()),
+                              __fadd_rn(__fadd_rn(__fmul_rn(mr, mr), __fmul_rn(mc, mc)), kC1()));
+  const float con = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.0f, sr), sc), kC2()),
+                              __fadd_rn(__fadd_rn(__fmul_rn(sr, sr), __fmul_rn(sc, sc)), kC2()));
+  const float str = __fdiv_rn(__fadd_rn(cross, kC3()), __fadd_rn(__fmul_rn(sr, sc), kC3()));
+  return __fmul_rn(__fmul_rn(lum, con), str);
+}
+
+// ssim.c:3-27 + :52 for a w x h rectangle of bytes (any address space)
+__device__ __forceinline__ void rect_stats(const uint8_t *p, int pitch, int w, int h, float area, float *mean,
+                                           float *stddev) {
+  int isum = 0;
+  for (int oy = 0; oy < h; oy++)
+    for (int ox = 0; ox < w; ox++) isum += p[oy * pitch + ox];
+  const float m = __fdiv_rn((float)isum, area);   // ssim.c:12 (the float sum of :9 is exact)
+  float vs = 0.0f;
+  for (int oy = 0; oy < h; oy++)
+    for (int ox = 0; ox < w; ox++) {
+      const float d = __fsub_rn((float)p[oy * pitch + ox], m);  // ssim.c:22
+      vs = __fadd_rn(vs, __fmul_rn(d, d));
+    }
+  *mean = m;
+  *stddev = __fsqrt_rn(__fdiv_rn(vs, area));      // ssim.c:25, :52
+}
+
+__device__ __forceinline__ unsigned long long shfl_max_u64(unsigned long long v) {
+  for (int off = 16; off; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------ generic kernel
+constexpr int kGenThreads = 256;
+
+__global__ void __launch_bounds__(kGenThreads)
+ssim_generic_kernel(Geom g, Frames f, Out o, int bx_begin, int bx_count, int smem_window_ok) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ unsigned long long warp_best[kGenThreads / 32];
+
+  const int pair = blockIdx.y;
+  const int bx = bx_begin + (int)(blockIdx.x % (unsigned)bx_count);
+  const int by = g.by_begin + (int)(blockIdx.x / (unsigned)bx_count);
+  const int bi = by * g.nbx + bx;
+  const int x0 = bx * g.B, y0 = by * g.B;
+  const int w = min(g.B, g.W - x0), h = min(g.B, g.H - y0);
+  // clamped window, inclusive bounds (main_ssim.c:22-25)
+  const int wx0 = max(0, x0 - g.R), wy0 = max(0, y0 - g.R);
+  const int wx1 = min(g.W - 1, x0 + w - 1 + g.R), wy1 = min(g.H - 1, y0 + h - 1 + g.R);
+  const int ncx = wx1 - w + 1 - wx0 + 1, ncy = wy1 - h + 1 - wy0 + 1;
+  const int ww = wx1 - wx0 + 1, wh = wy1 - wy0 + 1;
+
+  const uint8_t *cur = f.cur + (size_t)pair * f.pair_stride;
+  const uint8_t *ref = f.ref + (size_t)pair * f.pair_stride;
+
+  uint8_t *s_cur = smem;
+  for (int i = threadIdx.x; i < w * h; i += kGenThreads) {
+    const int r = i / w, c = i - r * w;
+    s_cur[i] = cur[(size_t)(y0 + r) * f.pitch + x0 + c];
+  }
+  const uint8_t *wbase;
+  int wpitch;
+  if (smem_window_ok) {
+    uint8_t *s_win = smem + ((w * h + 15) & ~15);
+    for (int i = threadIdx.x; i < ww * wh; i += kGenThreads) {
+      const int r = i / ww, c = i - r * ww;
+      s_win[i] = ref[(size_t)(wy0 + r) * f.pitch + wx0 + c];
+    }
+    wbase = s_win;
+    wpitch = ww;
+  } else {
+    wbase = ref + (size_t)wy0 * f.pitch + wx0;
+    wpitch = (int)f.pitch;
+  }
+  __syncthreads();
+
+  const float area = (float)(w * h);
+  // statistics of the current block (ssim.c:49,51,53): the same for every candidate; every
+  // thread derives them itself (a broadcast read of the block, no second barrier)
+  float mc, sc;
+  rect_stats(s_cur, w, w, h, area, &mc, &sc);
+  const int imc = (int)mc;                       // ssim.c:54: float -> int at the call
+  const bool exact_cross = w * h <= 258;
+
+  unsigned long long best = 0ull;
+  const int ncand = ncx * ncy;
+  for (int c = threadIdx.x; c < ncand; c += kGenThreads) {
+    const int cy = c / ncx, cx = c - cy * ncx;
+    const uint8_t *cand = wbase + cy * wpitch + cx;
+    float mr, sr;
+    rect_stats(cand, wpitch, w, h, area, &mr, &sr);
+    const int imr = (int)mr;
+    float cross;
+    if (exact_cross) {
+      int is = 0;
+      for (int oy = 0; oy < h; oy++)
+        for (int ox = 0; ox < w; ox++)
+          is += ((int)cand[oy * wpitch + ox] - imr) * ((int)s_cur[oy * w + ox] - imc);
+      cross = __fdiv_rn((float)is, area);
+    } else {
+      float fs = 0.0f;                           // ssim.c:36, literal
+      for (int oy = 0; oy < h; oy++)
+        for (int ox = 0; ox < w; ox++)
+          fs = __fadd_rn(fs, (float)(((int)cand[oy * wpitch + ox] - imr) * ((int)s_cur[oy * w + ox] - imc)));
+      cross = __fdiv_rn(fs, area);
+    }
+    const float s = ssim_from_stats(mr, sr, mc, sc, cross);
+    if (s > 0.0f) {                              // ssim.c:101 against the initial 0 (:88)
+      const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - (uint32_t)c);
+      best = key > best ? key : best;
+    }
+  }
+  best = shfl_max_u64(best);
+  if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kGenThreads / 32; i++) best = warp_best[i] > best ? warp_best[i] : best;
+    const size_t oi = (size_t)pair * g.nbx * g.nby + bi;
+    int mvx = 0, mvy = 0;
+    if (best != 0ull) {
+      const int c = (int)(0xffffffffu - (uint32_t)best);
+      const int cy = c / ncx, cx = c - cy * ncx;
+      mvx = wx0 + cx - x0;                       // ssim.c:103
+      mvy = wy0 + cy - y0;                       // ssim.c:104
+    }
+    if (o.mvx) o.mvx[oi] = mvx;
+    if (o.mvy) o.mvy[oi] = mvy;
+    if (o.ssd) o.ssd[oi] = best != 0ull ? 1u : 0u;
+    if (o.score) o.score[oi] = __uint_as_float((uint32_t)(best >> 32));
+  }
+}
+
+// ------------------------------------------------------------------ statistics pre-pass
+// One thread per position (x, y) of the table = top-left corner of a BxB rectangle of the
+// reference frame.  A CTA covers kSx x kSy positions and stages the pixels it needs as floats
+// (the conversion is exact), so the two raster passes are LDS + 1 resp. 3 float operations
+// per pixel.  Rectangles that leave the frame are not candidates of any block: skipped.
+constexpr int kSx = 64, kSy = 4;
+
+template <int B>
+__global__ void __launch_bounds__(kSx * kSy)
+ssim_stats_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_stride, int W, int H, int y_lo,
+                  int y_hi, float2 *__restrict__ table, size_t table_pair_stride) {
+  __shared__ float px[kSy + B - 1][kSx + B - 1 + 1];
+  const int tx0 = blockIdx.x * kSx, ty0 = y_lo + blockIdx.y * kSy;
+  const uint8_t *src = ref + (size_t)blockIdx.z * pair_stride;
+  for (int i = threadIdx.x; i < (kSy + B - 1) * (kSx + B - 1); i += kSx * kSy) {
+    const int r = i / (kSx + B - 1), c = i - r * (kSx + B - 1);
+    const int y = ty0 + r, x = tx0 + c;
+    px[r][c] = (y < H && x < W) ? (float)src[(size_t)y * pitch + x] : 0.0f;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % kSx, ly = threadIdx.x / kSx;
+  const int x = tx0 + lx, y = ty0 + ly;
+  if (x + B > W || y + B > H || y > y_hi) return;
+  const float area = (float)(B * B);
+  float sum = 0.0f;                                  // ssim.c:5-11: integers < 2^24, exact
+#pragma unroll 1
+  for (int oy = 0; oy < B; oy++)
+#pragma unroll
+    for (int ox = 0; ox < B; ox++) sum = __fadd_rn(sum, px[ly + oy][lx + ox]);
+  const float m = __fdiv_rn(sum, area);              // ssim.c:12
+  float vs = 0.0f;                                   // ssim.c:18-24, raster order
+#pragma unroll 1
+  for (int oy = 0; oy < B; oy++)
+#pragma unroll
+    for (int ox = 0; ox < B; ox++) {
+      const float d = __fsub_rn(px[ly + oy][lx + ox], m);
+      vs = __fadd_rn(vs, __fmul_rn(d, d));
+    }
+  const float sd = __fsqrt_rn(__fdiv_rn(vs, area));  // ssim.c:25, :52
+  table[(size_t)blockIdx.z * table_pair_stride + (size_t)(y - y_lo) * W + x] = make_float2(m, sd);
+}
+
+// ------------------------------------------------------------------ tiled kernel
+constexpr int kTiledThreads = 256;
+constexpr int kTiledWarps = kTiledThreads / 32;
+
+struct SsimTiledParams {
+  int W, H, B, R;
+  int nbx, nby;
+  int by_begin;          // first block row of this launch
+  int nbx_full;          // blocks of full width per row (W / B)
+  int groups_per_row;    // ceil(nbx_full / GX)
+  int win_pitch;         // bytes per staged window row (multiple of 4)
+  int win_rows;          // 2R + B + VB (rows below the last candidate are zero)
+  int table_y_lo;        // frame row of the table's first row
+  size_t table_pair_stride;
+  const float2 *table;
+  Out out;
+};
+
+template <int WORDS, int BH, int GX, int VB>
+__global__ void __launch_bounds__(kTiledThreads, 2)
+ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
+  constexpr int BW = 4 * WORDS;
+  static_assert(kTiledWarps % GX == 0, "warps must divide evenly over the blocks of an item");
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ unsigned long long best_s[GX];
+  __shared__ float cur_mean[GX], cur_std[GX];
+  __shared__ int cur_sum[GX];
+
+  const int pair = blockIdx.z;
+  const int by = p.by_begin + blockIdx.y;
+  const int bx_first = blockIdx.x * GX;
+  const int nblk = min(GX, p.nbx_full - bx_first);
+  const int y0 = by * p.B, x_item = bx_first * BW;
+  const uint8_t *cur = f.cur + (size_t)pair * f.pair_stride;
+  const uint8_t *ref = f.ref + (size_t)pair * f.pair_stride;
+
+  // ---- stage the common window (origin x_item - R, y0 - R; zero outside the frame) and the
+  //      current blocks (GX * BW bytes per row)
+  uint8_t *s_win = smem;
+  uint8_t *s_cur = smem + p.win_pitch * p.win_rows;
+  const int wx_org = x_item - p.R, wy_org = y0 - p.R;
+  for (int i = threadIdx.x; i < (p.win_pitch >> 2) * p.win_rows; i += kTiledThreads) {
+    const int r = i / (p.win_pitch >> 2), c4 = (i - r * (p.win_pitch >> 2)) * 4;
+    const int y = wy_org + r;
+    uint32_t v = 0;
+    if (y >= 0 && y < p.H) {
+      const uint8_t *row = ref + (size_t)y * f.pitch;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int x = wx_org + c4 + b;
+        if (x >= 0 && x < p.W) v |= (uint32_t)row[x] << (8 * b);
+      }
+    }
+    reinterpret_cast<uint32_t *>(s_win)[i] = v;
+  }
+  for (int i = threadIdx.x; i < GX * WORDS * BH; i += kTiledThreads) {
+    const int r = i / (GX * WORDS), c4 = (i - r * (GX * WORDS)) * 4;
+    uint32_t v = 0;
+    if (x_item + c4 + 4 <= p.W) v = *reinterpret_cast<const uint32_t *>(cur + (size_t)(y0 + r) * f.pitch + x_item + c4);
+    reinterpret_cast<uint32_t *>(s_cur)[i] = v;
+  }
+  if (threadIdx.x < GX) best_s[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  // ---- statistics of the current blocks (ssim.c:49,51,53): one thread per block
+  if (threadIdx.x < nblk) {
+    float m, sd;
+    rect_stats(s_cur + threadIdx.x * BW, GX * BW, BW, BH, (float)(BW * BH), &m, &sd);
+    int isum = 0;
+    for (int oy = 0; oy < BH; oy++)
+      for (int ox = 0; ox < BW; ox++) isum += s_cur[oy * GX * BW + threadIdx.x * BW + ox];
+    cur_mean[threadIdx.x] = m;
+    cur_std[threadIdx.x] = sd;
+    cur_sum[threadIdx.x] = isum;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = warp % GX;                 // block of the item this warp works on
+  constexpr int kWarpsPerBlk = kTiledWarps / GX;
+  if (blk < nblk) {
+    const int x0 = x_item + blk * BW;
+    // clamped candidate range (main_ssim.c:22-25, ssim.c:98-99) as window-relative offsets
+    const int dx_lo = max(0, p.R - x0), dx_hi = min(2 * p.R, p.W - BW - x0 + p.R);
+    const int dy_lo = max(0, p.R - y0), dy_hi = min(2 * p.R, p.H - BH - y0 + p.R);
+    const int ncx = dx_hi - dx_lo + 1, ncy = dy_hi - dy_lo + 1;
+    const int ngy = (ncy + VB - 1) / VB;
+    const int ntasks = ncx * ngy;
+
+    uint32_t cw[BH][WORDS];
+#pragma unroll
+    for (int r = 0; r < BH; r++)
+#pragma unroll
+      for (int w = 0; w < WORDS; w++)
+        cw[r][w] = reinterpret_cast<const uint32_t *>(s_cur)[r * GX * WORDS + blk * WORDS + w];
+    const float mc = cur_mean[blk], sc = cur_std[blk];
+    const int imc = (int)mc, sumc = cur_sum[blk];
+    constexpr int n = BW * BH;
+    const float area = (float)n;
+
+    unsigned long long best = 0ull;
+    for (int t = (warp / GX) * 32 + lane; t < ntasks; t += kWarpsPerBlk * 32) {
+      const int gy = t / ncx, dxi = t - gy * ncx;
+      const int dx = dx_lo + dxi, dy0 = dy_lo + gy * VB;   // window-relative offsets of the first candidate
+      const int u = blk * BW + dx;                          // byte column inside a window row
+      const uint32_t shift = 8u * (uint32_t)(u & 3);
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(s_win + dy0 * p.win_pitch) + (u >> 2);
+      const int pitchw = p.win_pitch >> 2;
+      // table entries of the VB candidates (issued early; consumed after the dot products)
+      float2 st[VB];
+      {
+        const float2 *tp = p.table + (size_t)pair * p.table_pair_stride +
+                           (size_t)(y0 - p.R + dy0 - p.table_y_lo) * p.W + (x0 - p.R + dx);
+#pragma unroll
+        for (int v = 0; v < VB; v++)
+          st[v] = (dy0 + v <= dy_hi) ? __ldg(tp + (size_t)v * p.W) : make_float2(0.0f, 0.0f);
+      }
+      uint32_t acc[VB];
+#pragma unroll
+      for (int v = 0; v < VB; v++) acc[v] = 0u;
+#pragma unroll
+      for (int row = 0; row < BH + VB - 1; row++) {
+        uint32_t raw[WORDS + 1], rw[WORDS];
+#pragma unroll
+        for (int w = 0; w <= WORDS; w++) raw[w] = rowp[row * pitchw + w];
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) rw[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
+#pragma unroll
+        for (int v = 0; v < VB; v++) {
+          const int r = row - v;               // current-block row this window row meets for candidate v
+          if (r >= 0 && r < BH) {
+#pragma unroll
+            for (int w = 0; w < WORDS; w++) acc[v] = __dp4a(cw[r][w], rw[w], acc[v]);
+          }
+        }
+      }
+      // ---- float epilogue per candidate (ssim.c:54-58)
+#pragma unroll
+      for (int v = 0; v < VB; v++) {
+        if (dy0 + v <= dy_hi) {
+          const float mr = st[v].x, sr = st[v].y;
+          const int imr = (int)mr;                               // ssim.c:54 (ssim.h:12)
+          const int sumr = __float2int_rn(__fmul_rn(mr, area));  // n is a power of two: exact
+          const int is = (int)acc[v] - imr * sumc - imc * sumr + n * imr * imc;
+          const float cross = __fdiv_rn((float)is, area);        // ssim.c:39
+          const float s = ssim_from_stats(mr, sr, mc, sc, cross);
+          if (s > 0.0f) {
+            const uint32_t vis = (uint32_t)((dy0 + v - dy_lo) << 16) | (uint32_t)dxi;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - vis);
+            best = key > best ? key : best;
+          }
+        }
+      }
+    }
+    best = shfl_max_u64(best);
+    if (lane == 0 && best != 0ull) atomicMax(&best_s[blk], best);
+  }
+  __syncthreads();
+  if (threadIdx.x < nblk) {
+    const int bx = bx_first + threadIdx.x;
+    const int x0 = bx * BW;
+    const int dx_lo = max(0, p.R - x0), dy_lo = max(0, p.R - y0);
+    const unsigned long long key = best_s[threadIdx.x];
+    int mvx = 0, mvy = 0;
+    if (key != 0ull) {
+      const uint32_t vis = 0xffffffffu - (uint32_t)key;
+      mvx = dx_lo + (int)(vis & 0xffffu) - p.R;               // ssim.c:103
+      mvy = dy_lo + (int)(vis >> 16) - p.R;                   // ssim.c:104
+    }
+    const size_t oi = (size_t)pair * p.nbx * p.nby + (size_t)by * p.nbx + bx;
+    if (p.out.mvx) p.out.mvx[oi] = mvx;
+    if (p.out.mvy) p.out.mvy[oi] = mvy;
+    if (p.out.ssd) p.out.ssd[oi] = key != 0ull ? 1u : 0u;
+    if (p.out.score) p.out.score[oi] = __uint_as_float((uint32_t)(key >> 32));
+  }
+}
+
+cudaError_t launch_ssim_generic_rect(const Geom &g, const Frames &f, int npairs, const Out &o, int bx_begin,
+                                     int bx_count, int by_begin, int by_count, cudaStream_t s) {
+  if (bx_count <= 0 || by_count <= 0) return cudaSuccess;
+  const size_t cur_bytes = ((size_t)g.B * g.B + 15) & ~(size_t)15;
+  const size_t win_side = (size_t)g.B + 2 * (size_t)g.R;
+  const size_t win_bytes = win_side * win_side;
+  static const size_t kMaxSmem = 200 * 1024;
+  const int ok = cur_bytes + win_bytes <= kMaxSmem;
+  const size_t smem = ok ? cur_bytes + win_bytes : cur_bytes;
+  cudaError_t e =
+      cudaFuncSetAttribute(ssim_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+  if (e != cudaSuccess) return e;
+  Geom gb = g;
+  gb.by_begin = by_begin;
+  gb.by_count = by_count;
+  for (int done = 0; done < npairs; done += 65535) {
+    const int np = npairs - done > 65535 ? 65535 : npairs - done;
+    Frames ff = f;
+    ff.cur += (size_t)done * f.pair_stride;
+    ff.ref += (size_t)done * f.pair_stride;
+    Out oo = o;
+    const size_t off = (size_t)done * g.nbx * g.nby;
+    if (oo.mvx) oo.mvx += off;
+    if (oo.mvy) oo.mvy += off;
+    if (oo.ssd) oo.ssd += off;
+    if (oo.score) oo.score += off;
+    dim3 grid((unsigned)(bx_count * by_count), (unsigned)np);
+    ssim_generic_kernel<<<grid, kGenThreads, smem, s>>>(gb, ff, oo, bx_begin, bx_count, ok);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <int WORDS, int BH, int GX, int VB>
+cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin,
+                                    int by_count, cudaStream_t s, unsigned long long *launches) {
+  constexpr int BW = 4 * WORDS;
+  SsimTiledParams p;
+  p.W = g.W; p.H = g.H; p.B = g.B; p.R = g.R;
+  p.nbx = g.nbx; p.nby = g.nby;
+  p.by_begin = by_begin;
+  p.nbx_full = g.W / BW;
+  p.groups_per_row = (p.nbx_full + GX - 1) / GX;
+  p.win_pitch = (GX * BW + 2 * g.R + 4 + 3) & ~3;
+  p.win_rows = 2 * g.R + BH + VB;
+  p.out = o;
+  // statistics table: rows [y_lo, y_hi] of full-size positions that this band can touch
+  int y_lo = by_begin * g.B - g.R, y_hi = (by_begin + by_count - 1) * g.B + g.R;
+  if (y_lo < 0) y_lo = 0;
+  if (y_hi > g.H - BH) y_hi = g.H - BH;
+  const int nrows = y_hi - y_lo + 1;
+  p.table_y_lo = y_lo;
+  p.table_pair_stride = (size_t)g.W * nrows;
+  float2 *table = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&table, p.table_pair_stride * sizeof(float2) * (size_t)npairs + 256, s);
+  if (e != cudaSuccess) return e;
+  p.table = table;
+  const size_t ref_pair_stride = npairs > 1 ? f.pair_stride : f.pitch * g.H;
+  Frames ff = f;
+  ff.pair_stride = ref_pair_stride;
+  for (int done = 0; done < npairs && e == cudaSuccess; done += 65535) {
+    const int np = npairs - done > 65535 ? 65535 : npairs - done;
+    dim3 sg((g.W - BW + 1 + kSx - 1) / kSx, (nrows + kSy - 1) / kSy, np);
+    ssim_stats_kernel<BH><<<sg, kSx * kSy, 0, s>>>(f.ref + (size_t)done * ref_pair_stride, f.pitch, ref_pair_stride,
+                                                    g.W, g.H, y_lo, y_hi, table + (size_t)done * p.table_pair_stride,
+                                                    p.table_pair_stride);
+    (*launches)++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) break;
+    const int smem = p.win_pitch * p.win_rows + GX * BW * BH;
+    auto kern = ssim_tiled_kernel<WORDS, BH, GX, VB>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) break;
+    SsimTiledParams pp = p;
+    pp.table = table + (size_t)done * p.table_pair_stride;
+    const size_t off = (size_t)done * g.nbx * g.nby;
+    if (pp.out.mvx) pp.out.mvx += off;
+    if (pp.out.mvy) pp.out.mvy += off;
+    if (pp.out.ssd) pp.out.ssd += off;
+    if (pp.out.score) pp.out.score += off;
+    Frames fd = ff;
+    fd.cur += (size_t)done * ref_pair_stride;
+    fd.ref += (size_t)done * ref_pair_stride;
+    dim3 grid(p.groups_per_row, by_count, np);
+    kern<<<grid, kTiledThreads, smem, s>>>(pp, fd);
+    (*launches)++;
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(table, s);
+  return e;
+}
+
+}  // namespace
+
+bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur) {
+  if (g.B != 8 && g.B != 16) return false;
+  if (g.W < g.B || g.H < g.B) return false;
+  if (g.R > 1024) return false;
+  // current blocks are read as aligned 32-bit words
+  if ((pitch & 3) || (pair_stride & 3) || ((uintptr_t)cur & 3)) return false;
+  // window of one item + the current blocks must fit shared memory twice per SM
+  const size_t win = (size_t)(4 * g.B + 2 * g.R + 8) * (size_t)(2 * g.R + g.B + 8) + 4 * g.B * g.B;
+  return win <= 100 * 1024;
+}
+
+// SSIM-cost search of block rows [g.by_begin, g.by_begin + g.by_count).  tiled = false forces the
+// generic kernel for every block.  *launches is incremented per kernel launched.
+cudaError_t launch_ssim(const Geom &g, const Frames &f, int npairs, const Out &o, bool tiled, cudaStream_t s,
+                        unsigned long long *launches) {
+  unsigned long long dummy = 0;
+  if (!launches) launches = &dummy;
+  const int r0 = g.by_begin, r1 = g.by_begin + g.by_count;
+  if (!tiled || !ssim_tiled_supported(g, f.pitch, f.pair_stride, f.cur)) {
+    cudaError_t e = launch_ssim_generic_rect(g, f, npairs, o, 0, g.nbx, r0, g.by_count, s);
+    (*launches) += (unsigned long long)((npairs + 65534) / 65535);
+    return e;
+  }
+  const int full_rows = g.H / g.B, full_cols = g.W / g.B;
+  const int t1 = r1 < full_rows ? r1 : full_rows;
+  cudaError_t e = cudaSuccess;
+  if (t1 > r0) {
+    if (g.B == 16) e = launch_ssim_tiled_shape<4, 16, 4, 4>(g, f, npairs, o, r0, t1 - r0, s, launches);
+    else e = launch_ssim_tiled_shape<2, 8, 4, 8>(g, f, npairs, o, r0, t1 - r0, s, launches);
+    if (e != cudaSuccess) return e;
+    // partial-width blocks of the full-height rows
+    if (full_cols < g.nbx) {
+      e = launch_ssim_generic_rect(g, f, npairs, o, full_cols, g.nbx - full_cols, r0, t1 - r0, s);
+      (*launches) += (unsigned long long)((npairs + 65534) / 65535);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  if (r1 > full_rows) {  // partial-height bottom row
+    const int b0 = r0 > full_rows ? r0 : full_rows;
+    e = launch_ssim_generic_rect(g, f, npairs, o, 0, g.nbx, b0, r1 - b0, s);
+    (*launches) += (unsigned long long)((npairs + 65534) / 65535);
+  }
+  return e;
+}
+
+}  // namespace me

@@ -80,6 +80,18 @@ def far_pair(width: int, height: int, seed: int = 11):
             rng.integers(215, 256, (height, width), dtype=np.uint8))
 
 
+def inverted_pair(width: int, height: int, seed: int = 21, period: float = 37.0):
+    """Smooth texture vs its negative: every candidate of most blocks has a negative
+    cross-covariance, so no SSIM score exceeds 0 -- the case in which the reference's
+    SSIM scan never sets a motion vector (ssim.c:88-103)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.mgrid[0:height, 0:width]
+    ph = rng.uniform(0, 6.28, 3)
+    t = (np.sin(xx / period + ph[0]) + np.sin(yy / (0.8 * period) + ph[1]) + np.sin((xx + yy) / (1.7 * period) + ph[2]))
+    ref = np.clip(np.rint(128 + 40 * t + rng.normal(0, 1.0, t.shape)), 0, 255).astype(np.uint8)
+    return (255 - ref).astype(np.uint8), ref
+
+
 # ---- geometry / work counts (prediction_frame.c:9-23, main.c:53-54,73-76) -----------------
 
 def block_grid(width: int, height: int, blk_dim: int):

@@ -24,6 +24,8 @@ ME_ERR_NO_DEVICE = -4
 ME_ERR_NOMEM = -5
 ME_ERR_STATE = -6
 ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT = 0, 1, 2, 3
+ME_COST_MSE, ME_COST_SSIM = 0, 1
+ME_SEARCH_FULL, ME_SEARCH_THREE_STEP, ME_SEARCH_DIAMOND = 0, 1, 2
 ME_B200_MAX_SLOTS = 4
 
 PEAK_NAMES = ["IDP4A", "VABSDIFF4", "SSD_PAIR", "IADD3", "LOP3", "IMAD", "VIMNMX",
@@ -88,6 +90,15 @@ def load_library() -> C.CDLL:
         "me_b200_search_scores": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int,
                                             f32p, u32p]),
         "me_b200_release_cached": (None, []),
+        "me_b200_set_cost": (C.c_int, [vp, C.c_int]),
+        "me_b200_set_search": (C.c_int, [vp, C.c_int]),
+        "me_b200_fast_evaluations": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+        "me_b200_tss_first_step": (C.c_int, [C.c_int]),
+        "me_b200_search_ssim": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int]),
+        "me_b200_search_ssim_scores": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int,
+                                                 f32p, u32p]),
+        "me_b200_search_fast": (C.c_int, [C.POINTER(PredictionFrame), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                          f32p, u32p]),
         "me_b200_search_u8": (C.c_int, [vp, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_submit": (C.c_int, [vp, C.c_int, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_wait": (C.c_int, [vp, C.c_int]),
@@ -148,7 +159,8 @@ class Estimator:
     """
 
     def __init__(self, width: int, height: int, blk_dim: int = 8, extra_span: int = 12,
-                 device: int = 0, max_pairs: int = 1, kernel: int = ME_KERNEL_AUTO):
+                 device: int = 0, max_pairs: int = 1, kernel: int = ME_KERNEL_AUTO,
+                 cost: int = ME_COST_MSE, search: int = ME_SEARCH_FULL):
         self._lib = load_library()
         h = C.c_void_p()
         rc = self._lib.me_b200_create_ex(C.byref(h), device, width, height, blk_dim, extra_span,
@@ -161,6 +173,18 @@ class Estimator:
         self.num_blocks = self._lib.me_b200_num_blocks(h)
         self.blocks_x = self._lib.me_b200_blocks_x(h)
         self.blocks_y = self._lib.me_b200_blocks_y(h)
+        self.cost, self.search = cost, search
+        if cost != ME_COST_MSE:
+            self._check(self._lib.me_b200_set_cost(h, cost), "me_b200_set_cost")
+        if search != ME_SEARCH_FULL:
+            self._check(self._lib.me_b200_set_search(h, search), "me_b200_set_search")
+
+    @property
+    def fast_evaluations(self) -> int:
+        """Candidate evaluations of the fast searches run so far (synchronises the device)."""
+        v = C.c_uint64(0)
+        self._check(self._lib.me_b200_fast_evaluations(self._h, C.byref(v)), "me_b200_fast_evaluations")
+        return int(v.value)
 
     # -- bookkeeping -----------------------------------------------------------------
     def close(self):
@@ -291,18 +315,23 @@ def create_prediction_frame(cur_int: np.ndarray, width: int, height: int, blk_di
 
 
 def search_prediction_frame(pf: PredictionFrame, ref_int: np.ndarray, extra_span: int,
-                            want_scores: bool = False):
-    """The drop-in for ``main.c:144-158``: fills every block of ``pf``.
-    Returns (scores, ssd) arrays when ``want_scores``."""
+                            want_scores: bool = False, cost: int = ME_COST_MSE,
+                            search: int = ME_SEARCH_FULL):
+    """The drop-in for ``main.c:144-158`` (``cost=ME_COST_SSIM``: for the loop
+    ``main_ssim.c:67-77``; ``search`` = a fast pattern: see ``me_b200_search_fast``): fills
+    every block of ``pf``.  Returns (scores, ssd) arrays when ``want_scores``."""
     lib = load_library()
     assert ref_int.dtype == np.int32 and ref_int.flags.c_contiguous
     refp = ref_int.ctypes.data_as(C.POINTER(C.c_int))
-    if want_scores:
-        sc = np.empty(pf.num_blks, np.float32)
-        sd = np.empty(pf.num_blks, np.uint32)
+    sc = np.empty(pf.num_blks, np.float32) if want_scores else None
+    sd = np.empty(pf.num_blks, np.uint32) if want_scores else None
+    if search != ME_SEARCH_FULL:
+        rc = lib.me_b200_search_fast(C.byref(pf), refp, extra_span, search, _np_ptr(sc), _np_ptr(sd))
+    elif cost == ME_COST_SSIM:
+        rc = lib.me_b200_search_ssim_scores(C.byref(pf), refp, extra_span, _np_ptr(sc), _np_ptr(sd))
+    elif want_scores:
         rc = lib.me_b200_search_scores(C.byref(pf), refp, extra_span, _np_ptr(sc), _np_ptr(sd))
     else:
-        sc = sd = None
         rc = lib.me_b200_search(C.byref(pf), refp, extra_span)
     if rc != ME_OK:
         raise MeError(rc, "me_b200_search", lib.me_b200_last_error(None).decode())

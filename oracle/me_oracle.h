@@ -69,6 +69,25 @@ void me_oracle_frame_diff(const uint8_t *a, const uint8_t *b, int n, uint8_t *ou
 /* PSNR with peak = max pixel of both frames, 99.0 when identical (utils.c:137-164). */
 double me_oracle_psnr(const uint8_t *a, const uint8_t *b, int width, int height);
 
+/* ---- SSIM-cost full search (oracle/me_oracle_ssim.c; PINNED against the unmodified
+ * src/cpu/main_ssim.c + src/common/ssim.c).  Same arguments as me_oracle_search.
+ * out[].score = best SSIM (0 when no candidate scored above 0), out[].ssd = 1 when some
+ * candidate scored above 0, else 0 (the reference then leaves the MV uninitialised; (0,0) here). */
+int me_oracle_search_ssim(const uint8_t *cur, const uint8_t *ref,
+                          int width, int height, int blk_dim, int extra_span,
+                          int blk_begin, int blk_end, int nthreads,
+                          me_oracle_result *out);
+/* "Original Score" / "Compensated Score" of main_ssim.c:88-95 (float accumulation). */
+void me_oracle_ssim_frame_scores(const uint8_t *cur, const uint8_t *ref, const uint8_t *mc, int n,
+                                 float *original_score, float *compensated_score);
+
+/* ---- fast searches (oracle/me_oracle_fast.c; PARITY UNPINNED: absent from the reference,
+ * defined by that file).  algo 1 = three-step, 2 = diamond; MSE cost of main.c:18-27. */
+int me_oracle_search_fast(const uint8_t *cur, const uint8_t *ref, int width, int height, int blk_dim,
+                          int extra_span, int algo, int blk_begin, int blk_end, int nthreads,
+                          me_oracle_result *out, uint64_t *evaluated);
+int me_oracle_tss_first_step(int extra_span);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,29 @@ CASES = [
     ("far_64x64_16_8", "far", (64, 64, 13), 16, 8),         # 256 px: still exact
 ]
 
+# SSIM-cost full search (src/cpu/main_ssim.c + src/common/ssim.c); fixtures made by the unmodified
+# reference through tests/golden/make_golden_ssim.py
+SSIM_CASES = [
+    ("ssim_foreman_yf4_yf1_16_7", "foreman", (4, 1), 16, 7),    # main_ssim.c:41-42 defaults (blk 16, span 7)
+    ("ssim_foreman_yf4_yf1_4_15", "foreman", (4, 1), 4, 15),    # src/cpu/run_ssim.sh:4
+    ("ssim_foreman_yf2_yf1_8_12", "foreman", (2, 1), 8, 12),
+    ("ssim_foreman_yf2_yf1_16_32", "foreman", (2, 1), 16, 32),
+    ("ssim_foreman_yf2_yf1_5_7", "foreman", (2, 1), 5, 7),      # partial edge blocks
+    ("ssim_foreman_yf2_yf1_7_9", "foreman", (2, 1), 7, 9),
+    ("ssim_foreman_yf2_yf1_32_16", "foreman", (2, 1), 32, 16),  # w*h > 258: literal float cross sum
+    ("ssim_foreman_yf1_yf2_64_8", "foreman", (1, 2), 64, 8),
+    ("ssim_constant_96x64_8_12", "constant", (96, 64), 8, 12),  # every candidate scores exactly 1: first wins
+    ("ssim_noise_200x120_16_32", "shifted_noise", (200, 120, 99), 16, 32),
+    ("ssim_noise_96x64_16_64", "shifted_noise", (96, 64, 5), 16, 64),
+    ("ssim_noise_100x60_8_12", "shifted_noise", (100, 60, 7), 8, 12),   # partial right/bottom blocks, B = 8
+    ("ssim_random_64x48_8_4", "random", (64, 48, 3), 8, 4),
+    ("ssim_checker_64x64_32_8", "checker", (64, 64), 32, 8),
+    ("ssim_far_96x80_32_8", "far", (96, 80, 11), 32, 8),
+    ("ssim_far_64x64_16_8", "far", (64, 64, 13), 16, 8),
+    ("ssim_inverted_96x80_16_3", "inverted", (96, 80, 21), 16, 3),      # no candidate above 0
+    ("ssim_inverted_100x70_8_6", "inverted", (100, 70, 22), 8, 6),
+]
+
 
 def make_frames(gen, args):
     if gen == "foreman":
@@ -48,6 +71,8 @@ def make_frames(gen, args):
         return frames.far_pair(args[0], args[1], seed=args[2])
     if gen == "checker":
         return frames.checker_pair(*args)
+    if gen == "inverted":
+        return frames.inverted_pair(args[0], args[1], seed=args[2])
     raise ValueError(gen)
 
 
@@ -56,6 +81,13 @@ def load_golden():
     with open(os.path.join(HERE, "golden", "golden.json")) as f:
         meta = json.load(f)
     fields = np.load(os.path.join(HERE, "golden", "fields.npz"))
+    return meta, fields
+
+
+def load_golden_ssim():
+    with open(os.path.join(HERE, "golden", "golden_ssim.json")) as f:
+        meta = json.load(f)
+    fields = np.load(os.path.join(HERE, "golden", "fields_ssim.npz"))
     return meta, fields
 
 

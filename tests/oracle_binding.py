@@ -11,6 +11,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libme_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libme_ref.so")
+REF_SSIM_SO = os.path.join(ROOT, "oracle", "_ref", "libme_ref_ssim.so")
+TSS, DIAMOND = 1, 2
 
 RESULT_DTYPE = np.dtype([("mvx", np.int32), ("mvy", np.int32), ("ssd", np.uint32), ("score", np.float32)])
 
@@ -38,6 +40,16 @@ class Oracle:
         L.me_oracle_frame_diff.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.me_oracle_psnr.restype = C.c_double
         L.me_oracle_psnr.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.me_oracle_search_ssim.restype = C.c_int
+        L.me_oracle_search_ssim.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+        L.me_oracle_ssim_frame_scores.restype = None
+        L.me_oracle_ssim_frame_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.me_oracle_search_fast.restype = C.c_int
+        L.me_oracle_search_fast.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p,
+                                                                                       C.POINTER(C.c_uint64)]
+        L.me_oracle_tss_first_step.restype = C.c_int
+        L.me_oracle_tss_first_step.argtypes = [C.c_int]
 
     def num_blocks(self, W, H, B):
         return self.lib.me_oracle_num_blocks(W, H, B)
@@ -53,6 +65,44 @@ class Oracle:
         rc = self.lib.me_oracle_search(pc, pr, W, H, B, R, begin, end, nthreads, out.ctypes.data_as(C.c_void_p))
         assert rc == 0, rc
         return out
+
+    def search_ssim(self, cur, ref, B, R, begin=0, end=None, nthreads=None):
+        """SSIM-cost full search (main_ssim.c / ssim.c); 'ssd' = 1 when a candidate scored > 0."""
+        cur, pc = _u8(cur)
+        ref, pr = _u8(ref)
+        H, W = cur.shape
+        nb = self.num_blocks(W, H, B)
+        end = nb if end is None else end
+        out = np.zeros(end - begin, RESULT_DTYPE)
+        nthreads = nthreads or min(32, os.cpu_count() or 1)
+        rc = self.lib.me_oracle_search_ssim(pc, pr, W, H, B, R, begin, end, nthreads,
+                                            out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, rc
+        return out
+
+    def search_fast(self, cur, ref, B, R, algo, begin=0, end=None, nthreads=None):
+        """Three-step (algo 1) / diamond (algo 2) search as DEFINED by oracle/me_oracle_fast.c
+        (parity unpinned: the reference has no fast search).  Returns (results, evaluations)."""
+        cur, pc = _u8(cur)
+        ref, pr = _u8(ref)
+        H, W = cur.shape
+        nb = self.num_blocks(W, H, B)
+        end = nb if end is None else end
+        out = np.zeros(end - begin, RESULT_DTYPE)
+        ev = C.c_uint64(0)
+        nthreads = nthreads or min(32, os.cpu_count() or 1)
+        rc = self.lib.me_oracle_search_fast(pc, pr, W, H, B, R, algo, begin, end, nthreads,
+                                            out.ctypes.data_as(C.c_void_p), C.byref(ev))
+        assert rc == 0, rc
+        return out, int(ev.value)
+
+    def ssim_frame_scores(self, cur, ref, mc):
+        cur, pc = _u8(cur)
+        ref, pr = _u8(ref)
+        mc, pm = _u8(mc)
+        a, b = C.c_float(0), C.c_float(0)
+        self.lib.me_oracle_ssim_frame_scores(pc, pr, pm, cur.size, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def pixel_compares(self, W, H, B, R):
         return int(self.lib.me_oracle_pixel_compares(W, H, B, R))
@@ -131,6 +181,51 @@ class Ref:
         psnr = self.lib.ref_postprocess(pc, pr, W, H, B, mvx.ctypes.data_as(C.c_void_p),
                                         mvy.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         return out, psnr
+
+
+class RefSsim:
+    """The unmodified reference SSIM search (findBestBlkSSIM, main_ssim.c:16 / ssim.c)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_SSIM_SO)
+        L = self.lib
+        L.ref_ssim_search_blocks.restype = C.c_int
+        L.ref_ssim_search_blocks.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+        L.ref_ssim_score.restype = C.c_float
+        L.ref_ssim_score.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6
+        L.ref_ssim_postprocess.restype = None
+        L.ref_ssim_postprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SSIM_SO)
+
+    def search(self, cur, ref, B, R, begin=0, end=None, nthreads=None):
+        cur, pc = _u8(cur)
+        ref, pr = _u8(ref)
+        H, W = cur.shape
+        nb = (-(-W // B)) * (-(-H // B))
+        end = nb if end is None else end
+        out = np.zeros(end - begin, RESULT_DTYPE)
+        nthreads = nthreads or min(32, os.cpu_count() or 1)
+        rc = self.lib.ref_ssim_search_blocks(pc, pr, W, H, B, R, begin, end, nthreads,
+                                             out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return out
+
+    def output5(self, cur, ref, B, mvx, mvy):
+        cur, pc = _u8(cur)
+        ref, pr = _u8(ref)
+        H, W = cur.shape
+        mvx = np.ascontiguousarray(mvx, np.int32)
+        mvy = np.ascontiguousarray(mvy, np.int32)
+        out = np.zeros((5 * H, W), np.uint8)
+        a, b = C.c_float(0), C.c_float(0)
+        self.lib.ref_ssim_postprocess(pc, pr, W, H, B, mvx.ctypes.data_as(C.c_void_p),
+                                      mvy.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                      C.byref(a), C.byref(b))
+        return out, a.value, b.value
 
 
 def field_sha(mvx, mvy, ssd):
