@@ -49,7 +49,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
 
 // SSIM-cost full search (me_ssim.cu; reference: src/cpu/main_ssim.c + src/common/ssim.c).
 // Out.score = best SSIM, Out.ssd = 1 when some candidate scored above 0 (else MV = (0,0)).
-bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur);
+bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref);
 cudaError_t launch_ssim(const Geom &g, const Frames &f, int npairs, const Out &o, bool tiled, cudaStream_t s,
                         unsigned long long *launches);
 

@@ -187,45 +187,79 @@ ssim_generic_kernel(Geom g, Frames f, Out o, int bx_begin, int bx_count, int sme
 }
 
 // ------------------------------------------------------------------ statistics pre-pass
-// One thread per position (x, y) of the table = top-left corner of a BxB rectangle of the
-// reference frame.  A CTA covers kSx x kSy positions and stages the pixels it needs as floats
-// (the conversion is exact), so the two raster passes are LDS + 1 resp. 3 float operations
-// per pixel.  Rectangles that leave the frame are not candidates of any block: skipped.
-constexpr int kSx = 64, kSy = 4;
+// One thread per position (x, y) of the table = top-left corner of a BW x BH rectangle of the
+// reference frame; a CTA covers kSx x kSy positions.  The pixels it needs are staged as floats
+// (exact).  The pixel sum of ssim.c:3-11 is an exact integer: horizontal box sums are built
+// cooperatively, each position adds BH of them.  The variance (ssim.c:16-27) is the literal
+// raster-order float loop: LDS + FSUB + FMUL + FADD per pixel -- this is what the pre-pass costs
+// (1 KB of shared-memory reads and 768 dependent float operations per position).
+// Table entry = {pixel sum (int), stddev (float bits)}; mean = sum / (BW*BH) is exact to
+// recompute because BW*BH is a power of two.  Rectangles that leave the frame are not
+// candidates of any block: skipped.
+constexpr int kSx = 32, kSy = 8;
 
-template <int B>
+template <int BW, int BH>
 __global__ void __launch_bounds__(kSx * kSy)
 ssim_stats_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_stride, int W, int H, int y_lo,
-                  int y_hi, float2 *__restrict__ table, size_t table_pair_stride) {
-  __shared__ float px[kSy + B - 1][kSx + B - 1 + 1];
+                  int y_hi, int2 *__restrict__ table, size_t table_pair_stride) {
+  constexpr int TW = kSx + BW - 1, TH = kSy + BH - 1;
+  __shared__ float px[TH][TW];
+  __shared__ float hs[TH][kSx];
   const int tx0 = blockIdx.x * kSx, ty0 = y_lo + blockIdx.y * kSy;
   const uint8_t *src = ref + (size_t)blockIdx.z * pair_stride;
-  for (int i = threadIdx.x; i < (kSy + B - 1) * (kSx + B - 1); i += kSx * kSy) {
-    const int r = i / (kSx + B - 1), c = i - r * (kSx + B - 1);
+  for (int i = threadIdx.x; i < TH * TW; i += kSx * kSy) {
+    const int r = i / TW, c = i - r * TW;
     const int y = ty0 + r, x = tx0 + c;
     px[r][c] = (y < H && x < W) ? (float)src[(size_t)y * pitch + x] : 0.0f;
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < TH * kSx; i += kSx * kSy) {
+    const int r = i / kSx, c = i - r * kSx;
+    float a = 0.0f;
+#pragma unroll
+    for (int k = 0; k < BW; k++) a += px[r][c + k];   // integers <= 255*BW: exact in any order
+    hs[r][c] = a;
+  }
+  __syncthreads();
   const int lx = threadIdx.x % kSx, ly = threadIdx.x / kSx;
   const int x = tx0 + lx, y = ty0 + ly;
-  if (x + B > W || y + B > H || y > y_hi) return;
-  const float area = (float)(B * B);
+  if (x + BW > W || y + BH > H || y > y_hi) return;
+  const float area = (float)(BW * BH);
   float sum = 0.0f;                                  // ssim.c:5-11: integers < 2^24, exact
-#pragma unroll 1
-  for (int oy = 0; oy < B; oy++)
 #pragma unroll
-    for (int ox = 0; ox < B; ox++) sum = __fadd_rn(sum, px[ly + oy][lx + ox]);
+  for (int oy = 0; oy < BH; oy++) sum += hs[ly + oy][lx];
   const float m = __fdiv_rn(sum, area);              // ssim.c:12
   float vs = 0.0f;                                   // ssim.c:18-24, raster order
-#pragma unroll 1
-  for (int oy = 0; oy < B; oy++)
+#pragma unroll 2
+  for (int oy = 0; oy < BH; oy++)
 #pragma unroll
-    for (int ox = 0; ox < B; ox++) {
+    for (int ox = 0; ox < BW; ox++) {
       const float d = __fsub_rn(px[ly + oy][lx + ox], m);
       vs = __fadd_rn(vs, __fmul_rn(d, d));
     }
   const float sd = __fsqrt_rn(__fdiv_rn(vs, area));  // ssim.c:25, :52
-  table[(size_t)blockIdx.z * table_pair_stride + (size_t)(y - y_lo) * W + x] = make_float2(m, sd);
+  table[(size_t)blockIdx.z * table_pair_stride + (size_t)(y - y_lo) * W + x] =
+      make_int2((int)sum, (int)__float_as_uint(sd));
+}
+
+// Statistics of the CURRENT blocks (ssim.c:49,51,53) of the block rows of one launch: one thread
+// per block, literal raster-order variance straight from global memory.  Entry = {pixel sum,
+// stddev bits}; a serial chain of BW*BH float additions per block that must not sit inside the
+// search kernel (it would idle a whole CTA behind one thread).
+template <int BW, int BH>
+__global__ void __launch_bounds__(128)
+ssim_block_stats_kernel(const uint8_t *__restrict__ cur, size_t pitch, size_t pair_stride, int B, int by_begin,
+                        int by_count, int nbx_full, int2 *__restrict__ out) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= nbx_full * by_count) return;
+  const int bx = i % nbx_full, row = i / nbx_full;
+  const uint8_t *p = cur + (size_t)blockIdx.y * pair_stride + (size_t)(by_begin + row) * B * pitch + (size_t)bx * BW;
+  float m, sd;
+  rect_stats(p, (int)pitch, BW, BH, (float)(BW * BH), &m, &sd);
+  int isum = 0;
+  for (int oy = 0; oy < BH; oy++)
+    for (int ox = 0; ox < BW; ox++) isum += p[(size_t)oy * pitch + ox];
+  out[(size_t)blockIdx.y * nbx_full * by_count + i] = make_int2(isum, (int)__float_as_uint(sd));
 }
 
 // ------------------------------------------------------------------ tiled kernel
@@ -237,24 +271,36 @@ struct SsimTiledParams {
   int nbx, nby;
   int by_begin;          // first block row of this launch
   int nbx_full;          // blocks of full width per row (W / B)
-  int groups_per_row;    // ceil(nbx_full / GX)
   int win_pitch;         // bytes per staged window row (multiple of 4)
-  int win_rows;          // 2R + B + VB (rows below the last candidate are zero)
+  int win_rows;          // 2R + BH + VB (rows below the last candidate are zero)
   int table_y_lo;        // frame row of the table's first row
   size_t table_pair_stride;
-  const float2 *table;
+  const int2 *table;
+  const int2 *blk_stats; // {sum, stddev bits} of the current blocks: [pair][row of this launch][bx < nbx_full]
+  int by_count;
   Out out;
 };
 
-template <int WORDS, int BH, int GX, int VB>
+// A finished candidate can only matter if its score can still reach the best score seen so far.
+// score = fl(fl(L*C)*S) with L, C <= 1 up to rounding (at most 1 + 6.1u each, u = 2^-24), hence
+// score <= (num/den) * (1 + 15.5u) for S = num/den > 0.  The test
+//     fl(num * (1 + 2^-19)) < fl(thr * den)
+// therefore proves score < thr (strictly: ties are never pruned, they are decided by the visit
+// index) without a division; with thr = 0 it rejects exactly the candidates with num < 0, whose
+// score cannot be above 0 (ssim.c:88,101).
+__device__ __forceinline__ float kPruneMargin() { return 1.0000019073486328125f; }  // 1 + 2^-19
+
+template <int WORDS, int BH, int GX, int VB, int PITCH>
 __global__ void __launch_bounds__(kTiledThreads, 2)
 ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
   constexpr int BW = 4 * WORDS;
+  constexpr int n = BW * BH;                  // a power of two for every instantiated shape
+  static_assert((n & (n - 1)) == 0, "block area must be a power of two");
   static_assert(kTiledWarps % GX == 0, "warps must divide evenly over the blocks of an item");
+  constexpr int kLogN = n == 256 ? 8 : n == 128 ? 7 : n == 64 ? 6 : n == 32 ? 5 : 4;
+  static_assert((1 << kLogN) == n, "unsupported block area");
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ unsigned long long best_s[GX];
-  __shared__ float cur_mean[GX], cur_std[GX];
-  __shared__ int cur_sum[GX];
 
   const int pair = blockIdx.z;
   const int by = p.by_begin + blockIdx.y;
@@ -264,24 +310,30 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
   const uint8_t *cur = f.cur + (size_t)pair * f.pair_stride;
   const uint8_t *ref = f.ref + (size_t)pair * f.pair_stride;
 
-  // ---- stage the common window (origin x_item - R, y0 - R; zero outside the frame) and the
-  //      current blocks (GX * BW bytes per row)
+  // ---- stage the common window and the current blocks (GX * BW bytes per row).  The window's
+  //      first column is the 4-aligned column at or left of x_item - R (e bytes of slack), so
+  //      interior words are single aligned 32-bit loads; everything outside the frame is zero.
+  // PITCH (bytes per staged row) is a compile-time constant so that every row offset of the
+  // streaming loop is an LDS immediate; only p.win_pitch bytes of a row are filled and read.
   uint8_t *s_win = smem;
-  uint8_t *s_cur = smem + p.win_pitch * p.win_rows;
-  const int wx_org = x_item - p.R, wy_org = y0 - p.R;
+  uint8_t *s_cur = smem + PITCH * p.win_rows;
+  const int e = (x_item - p.R) & 3;
+  const int wx_org = x_item - p.R - e, wy_org = y0 - p.R;
   for (int i = threadIdx.x; i < (p.win_pitch >> 2) * p.win_rows; i += kTiledThreads) {
     const int r = i / (p.win_pitch >> 2), c4 = (i - r * (p.win_pitch >> 2)) * 4;
-    const int y = wy_org + r;
+    const int y = wy_org + r, x = wx_org + c4;
     uint32_t v = 0;
     if (y >= 0 && y < p.H) {
       const uint8_t *row = ref + (size_t)y * f.pitch;
+      if (x >= 0 && x + 4 <= p.W) {
+        v = *reinterpret_cast<const uint32_t *>(row + x);
+      } else {
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int x = wx_org + c4 + b;
-        if (x >= 0 && x < p.W) v |= (uint32_t)row[x] << (8 * b);
+        for (int b = 0; b < 4; b++)
+          if (x + b >= 0 && x + b < p.W) v |= (uint32_t)row[x + b] << (8 * b);
       }
     }
-    reinterpret_cast<uint32_t *>(s_win)[i] = v;
+    reinterpret_cast<uint32_t *>(s_win)[r * (PITCH >> 2) + (c4 >> 2)] = v;
   }
   for (int i = threadIdx.x; i < GX * WORDS * BH; i += kTiledThreads) {
     const int r = i / (GX * WORDS), c4 = (i - r * (GX * WORDS)) * 4;
@@ -290,19 +342,6 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
     reinterpret_cast<uint32_t *>(s_cur)[i] = v;
   }
   if (threadIdx.x < GX) best_s[threadIdx.x] = 0ull;
-  __syncthreads();
-
-  // ---- statistics of the current blocks (ssim.c:49,51,53): one thread per block
-  if (threadIdx.x < nblk) {
-    float m, sd;
-    rect_stats(s_cur + threadIdx.x * BW, GX * BW, BW, BH, (float)(BW * BH), &m, &sd);
-    int isum = 0;
-    for (int oy = 0; oy < BH; oy++)
-      for (int ox = 0; ox < BW; ox++) isum += s_cur[oy * GX * BW + threadIdx.x * BW + ox];
-    cur_mean[threadIdx.x] = m;
-    cur_std[threadIdx.x] = sd;
-    cur_sum[threadIdx.x] = isum;
-  }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,6 +355,9 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
     const int ncx = dx_hi - dx_lo + 1, ncy = dy_hi - dy_lo + 1;
     const int ngy = (ncy + VB - 1) / VB;
     const int ntasks = ncx * ngy;
+    // start with the group of rows that holds zero motion (dy = R): on real video the best scores
+    // sit there, so the pruning threshold is high from the first tasks on
+    const int gy_first = (p.R - dy_lo) / VB;
 
     uint32_t cw[BH][WORDS];
 #pragma unroll
@@ -323,61 +365,76 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
 #pragma unroll
       for (int w = 0; w < WORDS; w++)
         cw[r][w] = reinterpret_cast<const uint32_t *>(s_cur)[r * GX * WORDS + blk * WORDS + w];
-    const float mc = cur_mean[blk], sc = cur_std[blk];
-    const int imc = (int)mc, sumc = cur_sum[blk];
-    constexpr int n = BW * BH;
-    const float area = (float)n;
+    const float inv_n = 1.0f / (float)n;                  // exact: dividing by n == multiplying by it
+    const int2 cs = __ldg(p.blk_stats + ((size_t)pair * p.by_count + blockIdx.y) * p.nbx_full + bx_first + blk);
+    const float mc = __fmul_rn((float)cs.x, inv_n), sc = __int_as_float(cs.y);   // ssim.c:49,53
+    const int imc = cs.x >> kLogN;                        // (int)mean, ssim.c:54 (ssim.h:12)
+    const int A = cs.x - n * imc;                         // sum (c - imc)
 
     unsigned long long best = 0ull;
-    for (int t = (warp / GX) * 32 + lane; t < ntasks; t += kWarpsPerBlk * 32) {
-      const int gy = t / ncx, dxi = t - gy * ncx;
-      const int dx = dx_lo + dxi, dy0 = dy_lo + gy * VB;   // window-relative offsets of the first candidate
-      const int u = blk * BW + dx;                          // byte column inside a window row
-      const uint32_t shift = 8u * (uint32_t)(u & 3);
-      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(s_win + dy0 * p.win_pitch) + (u >> 2);
-      const int pitchw = p.win_pitch >> 2;
-      // table entries of the VB candidates (issued early; consumed after the dot products)
-      float2 st[VB];
-      {
-        const float2 *tp = p.table + (size_t)pair * p.table_pair_stride +
+    for (int base = (warp / GX) * 32; base < ntasks; base += kWarpsPerBlk * 32) {
+      // pruning threshold: the best score any lane of this warp has seen (positive floats order
+      // like their bit patterns)
+      const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, (uint32_t)(best >> 32)));
+      const int t = base + lane;
+      if (t < ntasks) {
+        int gy = t / ncx;
+        const int dxi = t - gy * ncx;
+        gy += gy_first;
+        if (gy >= ngy) gy -= ngy;
+        const int dx = dx_lo + dxi, dy0 = dy_lo + gy * VB;   // window-relative offsets of the first candidate
+        const int u = e + blk * BW + dx;                      // byte column inside a window row
+        const uint32_t shift = 8u * (uint32_t)(u & 3);
+        const uint32_t *rowp = reinterpret_cast<const uint32_t *>(s_win + dy0 * PITCH) + (u >> 2);
+        constexpr int pitchw = PITCH >> 2;
+        // table entries of the VB candidates (issued early; consumed after the dot products)
+        int2 st[VB];
+        {
+          const int2 *tp = p.table + (size_t)pair * p.table_pair_stride +
                            (size_t)(y0 - p.R + dy0 - p.table_y_lo) * p.W + (x0 - p.R + dx);
 #pragma unroll
-        for (int v = 0; v < VB; v++)
-          st[v] = (dy0 + v <= dy_hi) ? __ldg(tp + (size_t)v * p.W) : make_float2(0.0f, 0.0f);
-      }
-      uint32_t acc[VB];
+          for (int v = 0; v < VB; v++)
+            st[v] = (dy0 + v <= dy_hi) ? __ldg(tp + (size_t)v * p.W) : make_int2(0, 0);
+        }
+        uint32_t acc[VB];
 #pragma unroll
-      for (int v = 0; v < VB; v++) acc[v] = 0u;
+        for (int v = 0; v < VB; v++) acc[v] = 0u;
 #pragma unroll
-      for (int row = 0; row < BH + VB - 1; row++) {
-        uint32_t raw[WORDS + 1], rw[WORDS];
+        for (int row = 0; row < BH + VB - 1; row++) {
+          uint32_t raw[WORDS + 1], rw[WORDS];
 #pragma unroll
-        for (int w = 0; w <= WORDS; w++) raw[w] = rowp[row * pitchw + w];
+          for (int w = 0; w <= WORDS; w++) raw[w] = rowp[row * pitchw + w];
 #pragma unroll
-        for (int w = 0; w < WORDS; w++) rw[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
+          for (int w = 0; w < WORDS; w++) rw[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
 #pragma unroll
-        for (int v = 0; v < VB; v++) {
-          const int r = row - v;               // current-block row this window row meets for candidate v
-          if (r >= 0 && r < BH) {
+          for (int v = 0; v < VB; v++) {
+            const int r = row - v;             // current-block row this window row meets for candidate v
+            if (r >= 0 && r < BH) {
 #pragma unroll
-            for (int w = 0; w < WORDS; w++) acc[v] = __dp4a(cw[r][w], rw[w], acc[v]);
+              for (int w = 0; w < WORDS; w++) acc[v] = __dp4a(cw[r][w], rw[w], acc[v]);
+            }
           }
         }
-      }
-      // ---- float epilogue per candidate (ssim.c:54-58)
+        // ---- per candidate: cross term, cheap bound, and only then the full score (ssim.c:54-58)
 #pragma unroll
-      for (int v = 0; v < VB; v++) {
-        if (dy0 + v <= dy_hi) {
-          const float mr = st[v].x, sr = st[v].y;
-          const int imr = (int)mr;                               // ssim.c:54 (ssim.h:12)
-          const int sumr = __float2int_rn(__fmul_rn(mr, area));  // n is a power of two: exact
-          const int is = (int)acc[v] - imr * sumc - imc * sumr + n * imr * imc;
-          const float cross = __fdiv_rn((float)is, area);        // ssim.c:39
-          const float s = ssim_from_stats(mr, sr, mc, sc, cross);
-          if (s > 0.0f) {
-            const uint32_t vis = (uint32_t)((dy0 + v - dy_lo) << 16) | (uint32_t)dxi;
-            const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - vis);
-            best = key > best ? key : best;
+        for (int v = 0; v < VB; v++) {
+          if (dy0 + v <= dy_hi) {
+            const int sumr = st[v].x;
+            const float sr = __int_as_float(st[v].y);
+            const int imr = sumr >> kLogN;                             // (int)mean, ssim.c:54
+            const int is = (int)acc[v] - imr * A - imc * sumr;          // sum (r - imr)(c - imc), exact
+            const float cross = __fmul_rn((float)is, inv_n);            // ssim.c:39
+            const float num = __fadd_rn(cross, kC3());
+            const float den = __fadd_rn(__fmul_rn(sr, sc), kC3());
+            if (!(__fmul_rn(num, kPruneMargin()) < __fmul_rn(thr, den))) {
+              const float mr = __fmul_rn((float)sumr, inv_n);           // ssim.c:12
+              const float s = ssim_from_stats(mr, sr, mc, sc, cross);
+              if (s > 0.0f) {
+                const uint32_t vis = (uint32_t)((dy0 + v - dy_lo) << 16) | (uint32_t)dxi;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - vis);
+                best = key > best ? key : best;
+              }
+            }
           }
         }
       }
@@ -439,8 +496,10 @@ cudaError_t launch_ssim_generic_rect(const Geom &g, const Frames &f, int npairs,
   return cudaSuccess;
 }
 
-template <int WORDS, int BH, int GX, int VB>
-cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin,
+// Block rows [by_begin, by_begin + by_count) whose blocks are BW x BH pixels (the full rows, or the
+// single partial-height bottom row when its height is a supported shape); full-width blocks only.
+template <int WORDS, int BH, int GX, int VB, int PITCH>
+cudaError_t launch_ssim_tiled_pitch(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin,
                                     int by_count, cudaStream_t s, unsigned long long *launches) {
   constexpr int BW = 4 * WORDS;
   SsimTiledParams p;
@@ -448,39 +507,52 @@ cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, 
   p.nbx = g.nbx; p.nby = g.nby;
   p.by_begin = by_begin;
   p.nbx_full = g.W / BW;
-  p.groups_per_row = (p.nbx_full + GX - 1) / GX;
-  p.win_pitch = (GX * BW + 2 * g.R + 4 + 3) & ~3;
+  const int groups_per_row = (p.nbx_full + GX - 1) / GX;
+  p.win_pitch = (GX * BW + 2 * g.R + 4 + 3 + 4) & ~3;  // + alignment slack on the left
   p.win_rows = 2 * g.R + BH + VB;
   p.out = o;
-  // statistics table: rows [y_lo, y_hi] of full-size positions that this band can touch
+  // statistics table: rows [y_lo, y_hi] of the positions that this band can touch
   int y_lo = by_begin * g.B - g.R, y_hi = (by_begin + by_count - 1) * g.B + g.R;
   if (y_lo < 0) y_lo = 0;
   if (y_hi > g.H - BH) y_hi = g.H - BH;
   const int nrows = y_hi - y_lo + 1;
   p.table_y_lo = y_lo;
   p.table_pair_stride = (size_t)g.W * nrows;
-  float2 *table = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&table, p.table_pair_stride * sizeof(float2) * (size_t)npairs + 256, s);
+  p.by_count = by_count;
+  const size_t blk_entries = (size_t)p.nbx_full * by_count;
+  int2 *table = nullptr;
+  cudaError_t e = cudaMallocAsync(
+      (void **)&table, (p.table_pair_stride + blk_entries) * sizeof(int2) * (size_t)npairs + 256, s);
   if (e != cudaSuccess) return e;
   p.table = table;
+  int2 *blk_stats = table + p.table_pair_stride * (size_t)npairs;
   const size_t ref_pair_stride = npairs > 1 ? f.pair_stride : f.pitch * g.H;
   Frames ff = f;
   ff.pair_stride = ref_pair_stride;
   for (int done = 0; done < npairs && e == cudaSuccess; done += 65535) {
     const int np = npairs - done > 65535 ? 65535 : npairs - done;
     dim3 sg((g.W - BW + 1 + kSx - 1) / kSx, (nrows + kSy - 1) / kSy, np);
-    ssim_stats_kernel<BH><<<sg, kSx * kSy, 0, s>>>(f.ref + (size_t)done * ref_pair_stride, f.pitch, ref_pair_stride,
-                                                    g.W, g.H, y_lo, y_hi, table + (size_t)done * p.table_pair_stride,
-                                                    p.table_pair_stride);
+    ssim_stats_kernel<BW, BH><<<sg, kSx * kSy, 0, s>>>(f.ref + (size_t)done * ref_pair_stride, f.pitch,
+                                                       ref_pair_stride, g.W, g.H, y_lo, y_hi,
+                                                       table + (size_t)done * p.table_pair_stride,
+                                                       p.table_pair_stride);
     (*launches)++;
     e = cudaGetLastError();
     if (e != cudaSuccess) break;
-    const int smem = p.win_pitch * p.win_rows + GX * BW * BH;
-    auto kern = ssim_tiled_kernel<WORDS, BH, GX, VB>;
+    dim3 bg((unsigned)((blk_entries + 127) / 128), np);
+    ssim_block_stats_kernel<BW, BH><<<bg, 128, 0, s>>>(f.cur + (size_t)done * ref_pair_stride, f.pitch,
+                                                      ref_pair_stride, g.B, by_begin, by_count, p.nbx_full,
+                                                      blk_stats + (size_t)done * blk_entries);
+    (*launches)++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) break;
+    const int smem = PITCH * p.win_rows + GX * BW * BH;
+    auto kern = ssim_tiled_kernel<WORDS, BH, GX, VB, PITCH>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) break;
     SsimTiledParams pp = p;
     pp.table = table + (size_t)done * p.table_pair_stride;
+    pp.blk_stats = blk_stats + (size_t)done * blk_entries;
     const size_t off = (size_t)done * g.nbx * g.nby;
     if (pp.out.mvx) pp.out.mvx += off;
     if (pp.out.mvy) pp.out.mvy += off;
@@ -489,7 +561,7 @@ cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, 
     Frames fd = ff;
     fd.cur += (size_t)done * ref_pair_stride;
     fd.ref += (size_t)done * ref_pair_stride;
-    dim3 grid(p.groups_per_row, by_count, np);
+    dim3 grid(groups_per_row, by_count, np);
     kern<<<grid, kTiledThreads, smem, s>>>(pp, fd);
     (*launches)++;
     e = cudaGetLastError();
@@ -498,17 +570,28 @@ cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, 
   return e;
 }
 
+// smallest instantiated row pitch that holds GX blocks + the span + alignment slack
+template <int WORDS, int BH, int GX, int VB>
+cudaError_t launch_ssim_tiled_shape(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin,
+                                    int by_count, cudaStream_t s, unsigned long long *launches) {
+  const int need = (GX * 4 * WORDS + 2 * g.R + 4 + 3 + 4) & ~3;
+  if (need <= 128) return launch_ssim_tiled_pitch<WORDS, BH, GX, VB, 128>(g, f, npairs, o, by_begin, by_count, s, launches);
+  if (need <= 208) return launch_ssim_tiled_pitch<WORDS, BH, GX, VB, 208>(g, f, npairs, o, by_begin, by_count, s, launches);
+  if (need <= 272) return launch_ssim_tiled_pitch<WORDS, BH, GX, VB, 272>(g, f, npairs, o, by_begin, by_count, s, launches);
+  return launch_ssim_tiled_pitch<WORDS, BH, GX, VB, 400>(g, f, npairs, o, by_begin, by_count, s, launches);
+}
+
 }  // namespace
 
-bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur) {
+bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
   if (g.B != 8 && g.B != 16) return false;
   if (g.W < g.B || g.H < g.B) return false;
-  if (g.R > 1024) return false;
-  // current blocks are read as aligned 32-bit words
-  if ((pitch & 3) || (pair_stride & 3) || ((uintptr_t)cur & 3)) return false;
+  if (g.R > 128) return false;  // row pitch 400 >= 8*16 + 2R + 11
+  // current blocks and window words are read as aligned 32-bit words
+  if ((pitch & 3) || (pair_stride & 3) || ((uintptr_t)cur & 3) || ((uintptr_t)ref & 3)) return false;
   // window of one item + the current blocks must fit shared memory twice per SM
-  const size_t win = (size_t)(4 * g.B + 2 * g.R + 8) * (size_t)(2 * g.R + g.B + 8) + 4 * g.B * g.B;
-  return win <= 100 * 1024;
+  const size_t win = (size_t)400 * (size_t)(2 * g.R + g.B + 8) + 8 * g.B * g.B;
+  return win <= 112 * 1024;
 }
 
 // SSIM-cost search of block rows [g.by_begin, g.by_begin + g.by_count).  tiled = false forces the
@@ -518,26 +601,39 @@ cudaError_t launch_ssim(const Geom &g, const Frames &f, int npairs, const Out &o
   unsigned long long dummy = 0;
   if (!launches) launches = &dummy;
   const int r0 = g.by_begin, r1 = g.by_begin + g.by_count;
-  if (!tiled || !ssim_tiled_supported(g, f.pitch, f.pair_stride, f.cur)) {
+  if (!tiled || !ssim_tiled_supported(g, f.pitch, f.pair_stride, f.cur, f.ref)) {
     cudaError_t e = launch_ssim_generic_rect(g, f, npairs, o, 0, g.nbx, r0, g.by_count, s);
     (*launches) += (unsigned long long)((npairs + 65534) / 65535);
     return e;
   }
   const int full_rows = g.H / g.B, full_cols = g.W / g.B;
+  const int hrem = g.H - full_rows * g.B;
   const int t1 = r1 < full_rows ? r1 : full_rows;
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
-    if (g.B == 16) e = launch_ssim_tiled_shape<4, 16, 4, 4>(g, f, npairs, o, r0, t1 - r0, s, launches);
-    else e = launch_ssim_tiled_shape<2, 8, 4, 8>(g, f, npairs, o, r0, t1 - r0, s, launches);
+    if (g.B == 16) e = launch_ssim_tiled_shape<4, 16, 8, 8>(g, f, npairs, o, r0, t1 - r0, s, launches);
+    else e = launch_ssim_tiled_shape<2, 8, 8, 8>(g, f, npairs, o, r0, t1 - r0, s, launches);
     if (e != cudaSuccess) return e;
-    // partial-width blocks of the full-height rows
-    if (full_cols < g.nbx) {
-      e = launch_ssim_generic_rect(g, f, npairs, o, full_cols, g.nbx - full_cols, r0, t1 - r0, s);
-      (*launches) += (unsigned long long)((npairs + 65534) / 65535);
+  }
+  int gen_bottom = 0;  // partial-height bottom row left to the generic kernel (all columns)
+  if (r1 > full_rows) {
+    // the bottom row of exactly half height (1080 = 67*16 + 8) is a tabulated shape of its own
+    if (hrem == g.B / 2 && r0 <= full_rows) {
+      if (g.B == 16) e = launch_ssim_tiled_shape<4, 8, 8, 8>(g, f, npairs, o, full_rows, 1, s, launches);
+      else e = launch_ssim_tiled_shape<2, 4, 8, 8>(g, f, npairs, o, full_rows, 1, s, launches);
       if (e != cudaSuccess) return e;
+    } else {
+      gen_bottom = 1;
     }
   }
-  if (r1 > full_rows) {  // partial-height bottom row
+  // partial-width blocks of every row the tiled launches covered
+  const int cover_end = gen_bottom ? t1 : r1;
+  if (full_cols < g.nbx && cover_end > r0) {
+    e = launch_ssim_generic_rect(g, f, npairs, o, full_cols, g.nbx - full_cols, r0, cover_end - r0, s);
+    (*launches) += (unsigned long long)((npairs + 65534) / 65535);
+    if (e != cudaSuccess) return e;
+  }
+  if (gen_bottom) {
     const int b0 = r0 > full_rows ? r0 : full_rows;
     e = launch_ssim_generic_rect(g, f, npairs, o, 0, g.nbx, b0, r1 - b0, s);
     (*launches) += (unsigned long long)((npairs + 65534) / 65535);

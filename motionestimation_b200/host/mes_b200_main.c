@@ -9,6 +9,9 @@
  * me_b200_search_scores().  In addition the per-block field the reference keeps
  * only in memory is written to <outdir>/mv_<blk>_<span>.txt:
  *   idx x0 y0 w h mvx mvy ssd score-bits(hex)
+ * Extra option (environment only, so the argv stays the reference's): ME_B200_SEARCH=tss or
+ * =diamond runs the three-step / diamond pattern instead of the exhaustive scan (not in the
+ * reference; see include/me_b200.h).
  * There is no CPU search in this program: without a GPU it reports the error
  * and exits 2.
  */
@@ -49,12 +52,19 @@ int main(int argc, char *argv[]) {
   float *scores = (float *)malloc(sizeof(float) * (size_t)p.num_blks);
   uint32_t *ssd = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)p.num_blks);
 
+  int pattern = ME_SEARCH_FULL;
+  const char *se = getenv("ME_B200_SEARCH");
+  if (se && !strcmp(se, "tss")) pattern = ME_SEARCH_THREE_STEP;
+  if (se && !strcmp(se, "diamond")) pattern = ME_SEARCH_DIAMOND;
+
   /* warm the context (device init, buffers) outside the timed region, as the
    * reference keeps thpool_init outside its timestamps (main.c:144,151) */
-  int rc = me_b200_search_scores(&p, ref, extraSpan, scores, ssd);
+  int rc = pattern == ME_SEARCH_FULL ? me_b200_search_scores(&p, ref, extraSpan, scores, ssd)
+                                     : me_b200_search_fast(&p, ref, extraSpan, pattern, scores, ssd);
   if (rc == ME_OK) {
     double t0 = getTimeStamp();
-    rc = me_b200_search_scores(&p, ref, extraSpan, scores, ssd);
+    rc = pattern == ME_SEARCH_FULL ? me_b200_search_scores(&p, ref, extraSpan, scores, ssd)
+                                   : me_b200_search_fast(&p, ref, extraSpan, pattern, scores, ssd);
     double t1 = getTimeStamp();
     if (rc == ME_OK) {
       int *out = (int *)calloc((size_t)n * 5, sizeof(int));

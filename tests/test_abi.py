@@ -102,6 +102,26 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
                        capture_output=True, text=True)
     assert p.returncode == 2 and "no usable CUDA device" in p.stderr
     assert not os.path.exists(tmp_path / "output_8_12.yuv")
+    # the SSIM program and the fast patterns have no CPU path either
+    exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200_ssim")
+    p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path), "16", "7", "352", "288"],
+                       capture_output=True, text=True)
+    assert p.returncode == 2 and "no usable CUDA device" in p.stderr
+    assert not os.path.exists(tmp_path / "output_16_7.yuv")
+
+
+@pytest.mark.skipif(me.device_count() > 0, reason="no-GPU behaviour")
+def test_ssim_and_fast_entry_points_need_a_device():
+    lib = me.load_library()
+    cur = np.zeros(64 * 48, np.int32)
+    pf = me.create_prediction_frame(cur, 64, 48, 8)
+    refp = cur.ctypes.data_as(C.POINTER(C.c_int))
+    assert lib.me_b200_search_ssim(C.byref(pf), refp, 4) == me.ME_ERR_NO_DEVICE
+    assert lib.me_b200_search_fast(C.byref(pf), refp, 4, me.ME_SEARCH_DIAMOND, None, None) == me.ME_ERR_NO_DEVICE
+    assert lib.me_b200_search_fast(C.byref(pf), refp, 4, 0, None, None) == me.ME_ERR_INVALID_ARG
+    assert lib.me_b200_set_cost(None, me.ME_COST_SSIM) == me.ME_ERR_INVALID_ARG
+    assert lib.me_b200_set_search(None, me.ME_SEARCH_DIAMOND) == me.ME_ERR_INVALID_ARG
+    assert lib.me_b200_tss_first_step(7) == 4 and lib.me_b200_tss_first_step(32) == 16
 
 
 def test_product_does_not_import_oracle():

@@ -2,11 +2,14 @@
 PARITY UNPINNED against the reference (it has no fast search): the kernels are compared bit for
 bit -- motion vectors, SSD, score bits, number of candidate evaluations -- with the definition in
 oracle/me_oracle_fast.c, which tests/test_oracle_fast.py pins on the CPU."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
 import motionestimation_b200 as me
-from oracle_binding import Oracle, TSS, DIAMOND
+from oracle_binding import Oracle, TSS, DIAMOND, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +96,20 @@ def test_fast_search_1080p_device_path(orc, algo, mode):
            "ssd": ssd.cpu().numpy().astype(np.uint32)[None], "score": score.cpu().numpy()[None]}
     check(out, 0, o, "1080p")
     assert evals == ev
+
+
+@pytest.mark.parametrize("algo,env", [(TSS, "tss"), (DIAMOND, "diamond")])
+def test_fast_search_cli(tmp_path, orc, algo, env):
+    """mes_b200 with ME_B200_SEARCH: the reference's argv, the fast pattern's field in mv_*.txt."""
+    exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200")
+    g = os.path.join(ROOT, "tests", "golden")
+    p = subprocess.run([exe, f"{g}/ForemanYF2.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path)],
+                       capture_output=True, text=True, env=dict(os.environ, ME_B200_SEARCH=env))
+    assert p.returncode == 0, p.stderr
+    o, _ = orc.search_fast(me.foreman(2), me.foreman(1), 8, 12, algo)
+    rows = [l.split() for l in open(tmp_path / "mv_8_12.txt")]
+    assert [int(r[5]) for r in rows] == o["mvx"].tolist() and [int(r[6]) for r in rows] == o["mvy"].tolist()
+    assert [int(r[7]) for r in rows] == o["ssd"].tolist()
+    out5, psnr = orc.output5(me.foreman(2), me.foreman(1), 8, o)
+    assert open(tmp_path / "output_8_12.yuv", "rb").read() == out5.tobytes()
+    assert "PSNR: %.6f\n" % psnr in p.stdout

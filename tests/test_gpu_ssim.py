@@ -2,12 +2,16 @@
 C ABI of libme_b200.so (context mode ME_COST_SSIM, or the me_b200_search_ssim drop-in) and is
 compared bit for bit -- motion vectors, found flag, float score bits -- with the fixtures made
 by the unmodified reference (tests/golden/*_ssim.*) and with the pinned restatement."""
+import hashlib
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
 import motionestimation_b200 as me
 from cases import SSIM_CASES, make_frames, load_golden_ssim
-from oracle_binding import Oracle
+from oracle_binding import Oracle, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -145,3 +149,24 @@ def test_ssim_mode_rules():
         assert lib.me_b200_set_search(est._h, me.ME_SEARCH_FULL) == me.ME_OK
         assert lib.me_b200_set_cost(est._h, me.ME_COST_SSIM) == me.ME_OK
         assert lib.me_b200_set_search(est._h, me.ME_SEARCH_THREE_STEP) == me.ME_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("args,name", [(("16", "7", "352", "288"), "ssim_foreman_yf4_yf1_16_7"),
+                                       (("4", "15", "352", "288"), "ssim_foreman_yf4_yf1_4_15")])
+def test_ssim_cli_is_byte_identical(tmp_path, args, name):
+    """mes_b200_ssim: same argv, same 'Original Score ... Compensated Score' line and the same
+    output_<B>_<R>.yuv bytes as the unmodified reference program (fixtures made from it)."""
+    exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200_ssim")
+    g = os.path.join(ROOT, "tests", "golden")
+    p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path), *args],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    m = META[name]
+    assert m["scores_line"] + "\n" in p.stdout
+    assert "Output file dimensions: (352 x 1440)" in p.stdout
+    out = open(tmp_path / f"output_{m['B']}_{m['R']}.yuv", "rb").read()
+    assert hashlib.md5(out).hexdigest() == m["yuv_md5"]
+    rows = [l.split() for l in open(tmp_path / f"mv_ssim_{m['B']}_{m['R']}.txt")]
+    assert [int(r[5]) for r in rows] == FIELDS[name + "/mvx"].tolist()
+    assert [int(r[6]) for r in rows] == FIELDS[name + "/mvy"].tolist()
+    assert [int(r[8], 16) for r in rows] == FIELDS[name + "/score_bits"].tolist()
