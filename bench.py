@@ -43,7 +43,17 @@ WORKLOADS = {
     "foreman_8x8_pm12": (352, 288, 8, 12, 512, "BASELINE configs[0]: Foreman YF2->YF1, reference defaults 8x8 +-12"),
     # the only configuration the reference publishes numbers for: 3840x2160, 8x8, +-12
     "4k_8x8_pm12": (3840, 2160, 8, 12, 16, "reference's own published runs: synthetic 3840x2160 luma, 8x8 blocks, full search +-12"),
+    # SSIM-cost full search (src/cpu/main_ssim.c); the first one is that program's default geometry
+    "ssim_4k_16x16_pm7": (3840, 2160, 16, 7, 8, "reference SSIM program defaults (main_ssim.c:41-44): synthetic 3840x2160 luma, blk 16, span 7"),
+    "ssim_1080p_16x16_pm32": (1920, 1080, 16, 32, 16, "SSIM-cost full search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),
+    # SURVEY 8 f-3 / BASELINE configs[3]: fast searches (absent from the reference; parity unpinned)
+    "tss_1080p_16x16_pm32": (1920, 1080, 16, 32, 64, "BASELINE configs[3]: three-step search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),
+    "diamond_1080p_16x16_pm32": (1920, 1080, 16, 32, 64, "BASELINE configs[3]: diamond search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),
+    "diamond_foreman_8x8_pm12": (352, 288, 8, 12, 512, "BASELINE configs[3]: diamond search, Foreman YF2->YF1, 8x8 blocks, +-12"),
 }
+# (cost, search pattern) of a workload: include/me_b200.h ME_COST_* / ME_SEARCH_*
+MODES = {"ssim_4k_16x16_pm7": (1, 0), "ssim_1080p_16x16_pm32": (1, 0), "tss_1080p_16x16_pm32": (0, 1),
+         "diamond_1080p_16x16_pm32": (0, 2), "diamond_foreman_8x8_pm12": (0, 2)}
 # published reference numbers for the exact same metric, frames/s of the search:
 # CPU Beauty 4K 8x8 +-12 = 2350 ms (results/cpu/beauty/2990wx_threadripper_64_cores.txt:12)
 PUBLISHED_FPS = {"4k_8x8_pm12": 1000.0 / 2350.0}
@@ -54,7 +64,7 @@ def make_batch(name, pairs, rank):
     """Deterministic synthetic batch (pairs, H, W) uint8 x2; a different seed per pair and rank."""
     import motionestimation_b200 as me
     W, H, B, R, _, _ = WORKLOADS[name]
-    if name.startswith("foreman"):
+    if "foreman" in name:
         c, r = me.foreman(2), me.foreman(1)
         return np.stack([c] * pairs), np.stack([r] * pairs)
     # a few distinct pairs, repeated: tiled Foreman (real texture/motion) + shifted noise
@@ -113,10 +123,14 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for n, b in bits.items() if seen & b]}
 
 
-def load_ref():
+def load_ref(mode=(0, 0)):
     """oracle/_ref (the unmodified reference, prebuilt) -- test/baseline infrastructure."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import Ref, Oracle
+    from oracle_binding import Ref, RefSsim, Oracle
+    if mode[1]:
+        return Oracle(), "port"          # fast searches do not exist in the reference
+    if mode[0] == 1:
+        return (RefSsim(), "reference") if RefSsim.available() else (Oracle(), "port")
     if Ref.available():
         return Ref(), "reference"
     return Oracle(), "port"
@@ -129,16 +143,24 @@ def cpu_reference_rate(name, budget_s, steps=1, warmup=0):
     W, H, B, R, _, _ = WORKLOADS[name]
     cur, ref = make_batch(name, 1, 0)
     cur, ref = cur[0], ref[0]
-    lib, kind = load_ref()
+    mode = MODES.get(name, (0, 0))
+    lib, kind = load_ref(mode)
     nbx, nby = -(-W // B), -(-H // B)
     nb = nbx * nby
 
     def run(b0, b1):
-        if kind == "reference":
+        if kind == "reference" and mode == (0, 0):
             sec, _ = lib.search_pool(cur, ref, B, R, b0, b1, pool_threads=100)
             return sec
         t0 = time.perf_counter()
-        lib.search(cur, ref, B, R, b0, b1, nthreads=os.cpu_count())
+        if mode[1]:
+            lib.search_fast(cur, ref, B, R, mode[1], b0, b1, nthreads=os.cpu_count())
+        elif mode[0] == 1 and kind == "reference":
+            lib.search(cur, ref, B, R, b0, b1, nthreads=os.cpu_count())   # unmodified findBestBlkSSIM
+        elif mode[0] == 1:
+            lib.search_ssim(cur, ref, B, R, b0, b1, nthreads=os.cpu_count())
+        else:
+            lib.search(cur, ref, B, R, b0, b1, nthreads=os.cpu_count())
         return time.perf_counter() - t0
 
     # probe with two interior block rows, then size the sample to the time budget
@@ -157,11 +179,18 @@ def cpu_reference_rate(name, budget_s, steps=1, warmup=0):
     t = float(np.mean(ts))
     blocks_s = (b1 - b0) / t
     cores = os.cpu_count() or 1
+    if mode == (0, 0):
+        how = ("reference thread pool of 100 (main.c:144), built -O2 from the unmodified sources "
+               "(src/cpu/run.sh:4 uses no -O)")
+    elif mode[1]:
+        how = ("CPU definition of the fast search (no reference implementation exists), one pthread per core")
+    else:
+        how = ("unmodified findBestBlkSSIM (main_ssim.c:16, ssim.c) built -O2, blocks split over one pthread per "
+               "core (the reference program itself runs them on one thread, main_ssim.c:67-77)")
     return blocks_s / nb, blocks_s, {
-        "kind": kind, "cores": cores, "threads": 100 if kind == "reference" else cores,
+        "kind": kind, "cores": cores, "threads": 100 if (kind == "reference" and mode == (0, 0)) else cores,
         "sample": f"{rows} of {nby} block rows ({b1 - b0} blocks) of one {W}x{H} pair, B={B} R={R}, "
-                  f"{steps} timed run(s) of {t * 1e3:.0f} ms; reference thread pool of 100 (main.c:144), "
-                  f"built -O2 from the unmodified sources (src/cpu/run.sh:4 uses no -O)",
+                  f"{steps} timed run(s) of {t * 1e3:.0f} ms; {how}",
         "ms_per_step": t * 1e3}
 
 
@@ -226,7 +255,8 @@ def main():
     cur_np, ref_np = make_batch(name, pairs, rank)
 
     slot_pairs = max(1, pairs // me.lib.ME_B200_MAX_SLOTS)
-    est = me.Estimator(W, H, B, R, device=local, max_pairs=slot_pairs)
+    cost, search = MODES.get(name, (0, 0))
+    est = me.Estimator(W, H, B, R, device=local, max_pairs=slot_pairs, cost=cost, search=search)
     nb = est.num_blocks
     pc_pair = est.pixel_compares
 
@@ -357,12 +387,24 @@ def main():
     if rank == 0:
         # ---- roofline of the search kernel (integer pipes) -----------------
         pair_rate, mhz = 0.0, 0.0
+        # MSE: VABSDIFF4 + IDP.4A pairs (2 ops per 4 pixels); SSIM: the only per-pixel work of a
+        # candidate is the dot product, 1 IDP.4A per 4 pixels, against the IDP.4A rate alone
+        which, per_pc, what = (0, 0.25, "IDP.4A") if cost == 1 else (2, 0.5, "VABSDIFF4+IDP.4A pairs")
         for _ in range(3):
-            r_, m_ = me.int_peak(2, iters=4000, device=local)    # VABSDIFF4 + IDP.4A pairs
+            r_, m_ = me.int_peak(which, iters=4000, device=local)
             if r_ > pair_rate:
                 pair_rate, mhz = r_, m_
         step_s = dev_ms / args.steps * 1e-3
-        lane_instr = 0.5 * pc_pair * pairs                       # algorithmic: 2 ops per 4 pixels
+        fast_evals = None
+        if search:
+            # a fast search evaluates a data-dependent handful of candidates per block
+            ev0 = est.fast_evaluations
+            step()
+            fast_evals = est.fast_evaluations - ev0
+            pc_step = fast_evals * B * B   # upper bound (partial edge blocks are smaller)
+        else:
+            pc_step = pc_pair * pairs
+        lane_instr = per_pc * pc_step                            # algorithmic lane-instructions per step
         achieved = lane_instr / step_s
         alg_bytes = pairs * (2 * W * H + 16 * nb)                # u8 cur + ref read once, 16 B/block out
         clocks = sampler.summary()
@@ -382,8 +424,11 @@ def main():
                        "pairs_per_gpu_per_step": pairs, "blocks_per_pair": nb,
                        "pixel_compares_per_pair": pc_pair, "parallelism": f"frame-pair sharding x{world}",
                        "l2": "inputs larger than L2" if flush is None else "L2 flushed between steps (192 MB write)",
-                       "kernel": {1: "generic", 2: "tiled"}[est.kernel_in_use]},
-            "blocks_per_s": fps * nb, "pixel_compares_per_s": fps * pc_pair,
+                       "kernel": ("warp-per-block fast search" if search else "ssim tiled + statistics pre-pass" if cost
+                                  else {1: "generic", 2: "tiled", 3: "direct"}[est.kernel_in_use]),
+                       "cost": ["mse", "ssim"][cost], "search": ["full", "three_step", "diamond"][search]},
+            "blocks_per_s": fps * nb, "pixel_compares_per_s": pc_step / step_s,
+            "candidate_evaluations_per_s": (fast_evals / step_s) if fast_evals is not None else None,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 2 * pairs * n,
                     "d2h_bytes_per_step": 3 * pairs * nb * 4,
                     "api": "me_b200_submit/me_b200_wait, pinned u8 host frames, %d slots x %d pairs" % (nslots, slot_pairs)},
@@ -394,8 +439,10 @@ def main():
             "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": pair_rate / 1e12,
                          "unit": "T lane-instr/s", "frac": achieved / pair_rate if pair_rate else None,
                          "traffic": traffic,
-                         "peak_source": "measured live: me_b200_int_peak(VABSDIFF4+IDP.4A pairs) at %.0f MHz" % mhz,
-                         "frac_of_single_pipe_peak": achieved / (pair_rate / 2) if pair_rate else None,
+                         "peak_source": "measured live: me_b200_int_peak(%s) at %.0f MHz" % (what, mhz),
+                         "frac_of_single_pipe_peak": (achieved / (pair_rate / 2) if pair_rate else None) if cost == 0 else None,
+                         "note": ("fast search: a few dependent steps per block, latency bound by design; "
+                                  "the fraction only says how little arithmetic a fast search needs") if search else None,
                          "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": 6455.9,
                                  "algorithmic_bytes_per_step": alg_bytes}},
             "clocks": clocks,

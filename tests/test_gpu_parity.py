@@ -251,8 +251,12 @@ def test_pipelined_submit_wait():
         for slot in range(4):
             raw = [lib.me_b200_host_alloc(sz) for sz in (2 * n, 2 * n, 8 * nb, 8 * nb, 8 * nb, 8 * nb)]
             assert all(raw)
-            C.memmove(raw[0], np.concatenate([cur8.ravel(), ref8.ravel()]).ctypes.data, 2 * n)
-            C.memmove(raw[1], np.concatenate([ref8.ravel(), ref8.ravel()]).ctypes.data, 2 * n)
+            # keep the temporaries alive across the copy (a bare `.ctypes.data` of a temporary
+            # is an address into memory that may already be freed)
+            src_cur = np.concatenate([cur8.ravel(), ref8.ravel()])
+            src_ref = np.concatenate([ref8.ravel(), ref8.ravel()])
+            C.memmove(raw[0], src_cur.ctypes.data, 2 * n)
+            C.memmove(raw[1], src_ref.ctypes.data, 2 * n)
             est.submit_ptr(slot, raw[0], raw[1], 2, raw[2], raw[3], raw[4], raw[5])
             bufs.append(raw)
         with pytest.raises(me.MeError) as ei:
