@@ -4,13 +4,13 @@
 //
 // Reference being replaced: the same main.c:18-82 scan as the tuned kernel; with so few
 // candidates the rotating-accumulator streaming of me_tiled.cu cannot amortise its set-up, so
-// this kernel maps one thread to one (block, candidate) pair instead:
+// this kernel maps B lanes to one (block, candidate) pair instead:
 //   * a CTA owns a 128 x 32 pixel tile of blocks (8 x 2 blocks of 16x16 or 16 x 4 blocks of 8x8);
 //     the current tile and the reference tile + R halo are staged in shared memory once with
 //     coalesced 16-byte loads (each frame byte is read from HBM ~1.1 times);
-//   * a thread scores candidates idx = tid, tid + 256, ... of the tile: per row, the aligned
+//   * a group of B lanes scores one (block, candidate) unit, one block row per lane: the aligned
 //     reference words around the candidate column are funnel-shifted into place and compared with
-//     VABSDIFF4.U8 + IDP.4A.U8.U8 (exact integer SSD);
+//     VABSDIFF4.U8 + IDP.4A.U8.U8 (exact integer SSD), the rows are added with shuffles;
 //   * key = ssd << 8 | raster index of the candidate in the (2R+1)^2 grid, one 32-bit shared
 //     atomicMin per candidate; the unsigned minimum is the reference's first strict minimum in
 //     y-major/x-minor order (main.c:53-62) because clamped-away candidates are simply skipped.
@@ -22,16 +22,20 @@ namespace {
 
 constexpr int kTX = 128, kTY = 32;  // tile of pixels per CTA
 constexpr int kMaxR = 4;
-constexpr int kRefPitch = kTX + 32;                 // >= 15 + kTX + 2R + 3, multiple of 16
+constexpr int kRefStage = kTX + 32;                 // staged bytes per reference row: >= 15 + kTX + 2R + 3, multiple of 16
+// Row pitches in 32-bit words are ODD (41, 33): the B lanes of a unit read B different rows at the
+// same column, and an odd word stride spreads them over B different banks.
+constexpr int kRefPitchW = kRefStage / 4 + 1;
+constexpr int kCurPitchW = kTX / 4 + 1;
 constexpr int kRefRows = kTY + 2 * kMaxR;
 constexpr int kThreads = 256;
 
-template <int B>
+template <int B, bool ROWSPLIT>
 __global__ void __launch_bounds__(kThreads)
 direct_search_kernel(Geom g, Frames f, Out o) {
   constexpr int NBX = kTX / B, NBY = kTY / B, NBLK = NBX * NBY, WPR = B / 4;
-  __shared__ __align__(16) uint8_t s_cur[kTY * kTX];
-  __shared__ __align__(16) uint8_t s_ref[kRefRows * kRefPitch];
+  __shared__ uint32_t s_cur[kTY * kCurPitchW];
+  __shared__ uint32_t s_ref[kRefRows * kRefPitchW];
   __shared__ uint32_t s_best[NBLK];
 
   const int R = g.R, nd = 2 * R + 1, ncand = nd * nd;
@@ -54,59 +58,140 @@ direct_search_kernel(Geom g, Frames f, Out o) {
       if (x + b >= 0 && x + b < g.W) w[b >> 2] |= (uint32_t)q[x + b] << (8 * (b & 3));
     return make_uint4(w[0], w[1], w[2], w[3]);
   };
-  for (int i = threadIdx.x; i < kTY * (kTX / 16); i += kThreads) {
-    const int r = i / (kTX / 16), k = i - r * (kTX / 16);
-    reinterpret_cast<uint4 *>(s_cur)[i] = load16(cur, tx0 + 16 * k, ty0 + r);
-  }
   // reference columns start at the 16-aligned column left of tx0 - R
   const int rx0 = (tx0 - R) & ~15;  // may be negative
   const int ex = tx0 - R - rx0;     // 0..15 bytes between the aligned origin and tx0 - R
-  for (int i = threadIdx.x; i < (kTY + 2 * R) * (kRefPitch / 16); i += kThreads) {
-    const int r = i / (kRefPitch / 16), k = i - r * (kRefPitch / 16);
-    reinterpret_cast<uint4 *>(s_ref)[r * (kRefPitch / 16) + k] = load16(ref, rx0 + 16 * k, ty0 - R + r);
+  // all global loads of a thread are issued before the first shared store, so their latencies
+  // overlap: one 16-byte piece of the current tile, up to two of the reference tile
+  static_assert(kTY * (kTX / 16) == kThreads, "one current-tile piece per thread");
+  constexpr int kRefPieces = (kRefRows * (kRefStage / 16) + kThreads - 1) / kThreads;
+  const int nref = (kTY + 2 * R) * (kRefStage / 16);
+  uint4 vc, vr[kRefPieces];
+  {
+    const int r = threadIdx.x / (kTX / 16), k = threadIdx.x - r * (kTX / 16);
+    vc = load16(cur, tx0 + 16 * k, ty0 + r);
+  }
+#pragma unroll
+  for (int j = 0; j < kRefPieces; j++) {
+    const int i = threadIdx.x + j * kThreads;
+    const int r = i / (kRefStage / 16), k = i - r * (kRefStage / 16);
+    vr[j] = i < nref ? load16(ref, rx0 + 16 * k, ty0 - R + r) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  {
+    const int r = threadIdx.x / (kTX / 16), k = threadIdx.x - r * (kTX / 16);
+    uint32_t *d = s_cur + r * kCurPitchW + 4 * k;
+    d[0] = vc.x; d[1] = vc.y; d[2] = vc.z; d[3] = vc.w;
+  }
+#pragma unroll
+  for (int j = 0; j < kRefPieces; j++) {
+    const int i = threadIdx.x + j * kThreads;
+    if (i < nref) {
+      const int r = i / (kRefStage / 16), k = i - r * (kRefStage / 16);
+      uint32_t *d = s_ref + r * kRefPitchW + 4 * k;
+      d[0] = vr[j].x; d[1] = vr[j].y; d[2] = vr[j].z; d[3] = vr[j].w;
+    }
   }
   if (threadIdx.x < NBLK) s_best[threadIdx.x] = 0xffffffffu;
   __syncthreads();
 
-  // one (block, candidate) pair per thread-iteration; candidates vary fastest
-  for (int idx = threadIdx.x; idx < NBLK * ncand; idx += kThreads) {
-    const int blk = idx / ncand, c = idx - blk * ncand;
-    const int by_ = blk / NBX, bx_ = blk - by_ * NBX;
-    const int dyi = c / nd, dxi = c - dyi * nd;          // window-relative offsets, mv = d - R
-    const int x0 = tx0 + bx_ * B, y0 = ty0 + by_ * B;    // block origin in the frame
-    if (x0 >= g.W || y0 >= y_end) continue;
-    const int w = min(B, g.W - x0), h = min(B, g.H - y0);
-    // clamped window (main.c:73-76): the candidate must lie inside the frame
-    const int cx = x0 + dxi - R, cy = y0 + dyi - R;
-    if (cx < 0 || cy < 0 || cx + w > g.W || cy + h > g.H) continue;
-    const int u = ex + bx_ * B + dxi;                    // byte column in s_ref rows
-    const uint32_t shift = 8u * (uint32_t)(u & 3);
-    const uint32_t *rp = reinterpret_cast<const uint32_t *>(s_ref) + (by_ * B + dyi) * (kRefPitch / 4) + (u >> 2);
-    const uint32_t *cp = reinterpret_cast<const uint32_t *>(s_cur) + (by_ * B) * (kTX / 4) + bx_ * WPR;
-    uint32_t ssd = 0;
-    for (int r = 0; r < h; r++) {
-      uint32_t raw[WPR + 1];
-#pragma unroll
-      for (int k = 0; k <= WPR; k++) raw[k] = rp[k];
-#pragma unroll
-      for (int k = 0; k < WPR; k++) {
-        uint32_t rv = __funnelshift_r(raw[k], raw[k + 1], shift);
-        uint32_t cv = cp[k];
-        // partial-width blocks: compare only the w valid columns (both zero-padded otherwise,
-        // but the reference side holds real pixels there)
-        if (w < B) {
-          const int left = w - 4 * k;
-          const uint32_t m = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
-          rv &= m;
-          cv &= m;
+  if constexpr (ROWSPLIT) {
+    // One (block, candidate) UNIT per group of B lanes, one block row per lane: with only 1..81
+    // candidates per block a whole-candidate-per-thread mapping leaves most of the CTA idle behind a
+    // few long dependent chains (at +-0 just 16 of 256 threads had work); split by rows, every lane
+    // does 5 LDS + 4 x (SHF, VABSDIFF4, IDP.4A), the group adds up with log2(B) shuffles and its
+    // first lane does the shared atomicMin.  Passes are uniform over the CTA, so the shuffles always
+    // run with the full mask.
+    constexpr int UPP = kThreads / B;                        // units per pass
+    const int lane_row = threadIdx.x % B, unit_in_pass = threadIdx.x / B;
+    const int total_units = NBLK * ncand;
+    for (int base = 0; base < total_units; base += UPP) {
+      const int unit = base + unit_in_pass;
+      uint32_t ssd = 0;
+      bool valid = false;
+      int blk = 0, c = 0;
+      if (unit < total_units) {
+        blk = unit / ncand;
+        c = unit - blk * ncand;
+        const int by_ = blk / NBX, bx_ = blk - by_ * NBX;
+        const int dyi = c / nd, dxi = c - dyi * nd;          // window-relative offsets, mv = d - R
+        const int x0 = tx0 + bx_ * B, y0 = ty0 + by_ * B;    // block origin in the frame
+        if (x0 < g.W && y0 < y_end) {
+          const int w = min(B, g.W - x0), h = min(B, g.H - y0);
+          // clamped window (main.c:73-76): the candidate must lie inside the frame
+          const int cx = x0 + dxi - R, cy = y0 + dyi - R;
+          valid = !(cx < 0 || cy < 0 || cx + w > g.W || cy + h > g.H);
+          if (valid && lane_row < h) {
+            const int u = ex + bx_ * B + dxi;                // byte column in s_ref rows
+            const uint32_t shift = 8u * (uint32_t)(u & 3);
+            const uint32_t *rp = s_ref + (by_ * B + dyi + lane_row) * kRefPitchW + (u >> 2);
+            const uint32_t *cp = s_cur + (by_ * B + lane_row) * kCurPitchW + bx_ * WPR;
+            uint32_t raw[WPR + 1];
+  #pragma unroll
+            for (int k = 0; k <= WPR; k++) raw[k] = rp[k];
+  #pragma unroll
+            for (int k = 0; k < WPR; k++) {
+              uint32_t rv = __funnelshift_r(raw[k], raw[k + 1], shift);
+              uint32_t cv = cp[k];
+              // partial-width blocks: compare only the w valid columns (both zero-padded otherwise,
+              // but the reference side holds real pixels there)
+              if (w < B) {
+                const int left = w - 4 * k;
+                const uint32_t m = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+                rv &= m;
+                cv &= m;
+              }
+              const uint32_t d = __vabsdiffu4(cv, rv);
+              ssd = __dp4a(d, d, ssd);
+            }
+          }
         }
-        const uint32_t d = __vabsdiffu4(cv, rv);
-        ssd = __dp4a(d, d, ssd);
       }
-      rp += kRefPitch / 4;
-      cp += kTX / 4;
+  #pragma unroll
+      for (int off = B / 2; off; off >>= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, off);
+      if (valid && lane_row == 0) atomicMin(&s_best[blk], (ssd << 8) | (uint32_t)c);
     }
-    atomicMin(&s_best[blk], (ssd << 8) | (uint32_t)c);
+  } else {
+  // one (block, candidate) pair per thread-iteration; candidates vary fastest (consecutive lanes
+    // read the same rows: broadcasts, no bank conflicts)
+    for (int idx = threadIdx.x; idx < NBLK * ncand; idx += kThreads) {
+      const int blk = idx / ncand, c = idx - blk * ncand;
+      const int by_ = blk / NBX, bx_ = blk - by_ * NBX;
+      const int dyi = c / nd, dxi = c - dyi * nd;          // window-relative offsets, mv = d - R
+      const int x0 = tx0 + bx_ * B, y0 = ty0 + by_ * B;    // block origin in the frame
+      if (x0 >= g.W || y0 >= y_end) continue;
+      const int w = min(B, g.W - x0), h = min(B, g.H - y0);
+      // clamped window (main.c:73-76): the candidate must lie inside the frame
+      const int cx = x0 + dxi - R, cy = y0 + dyi - R;
+      if (cx < 0 || cy < 0 || cx + w > g.W || cy + h > g.H) continue;
+      const int u = ex + bx_ * B + dxi;                    // byte column in s_ref rows
+      const uint32_t shift = 8u * (uint32_t)(u & 3);
+      const uint32_t *rp = s_ref + (by_ * B + dyi) * kRefPitchW + (u >> 2);
+      const uint32_t *cp = s_cur + (by_ * B) * kCurPitchW + bx_ * WPR;
+      uint32_t ssd = 0;
+      for (int r = 0; r < h; r++) {
+        uint32_t raw[WPR + 1];
+  #pragma unroll
+        for (int k = 0; k <= WPR; k++) raw[k] = rp[k];
+  #pragma unroll
+        for (int k = 0; k < WPR; k++) {
+          uint32_t rv = __funnelshift_r(raw[k], raw[k + 1], shift);
+          uint32_t cv = cp[k];
+          // partial-width blocks: compare only the w valid columns (both zero-padded otherwise,
+          // but the reference side holds real pixels there)
+          if (w < B) {
+            const int left = w - 4 * k;
+            const uint32_t m = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+            rv &= m;
+            cv &= m;
+          }
+          const uint32_t d = __vabsdiffu4(cv, rv);
+          ssd = __dp4a(d, d, ssd);
+        }
+        rp += kRefPitchW;
+        cp += kCurPitchW;
+      }
+      atomicMin(&s_best[blk], (ssd << 8) | (uint32_t)c);
+    }
   }
   __syncthreads();
 
@@ -152,8 +237,13 @@ cudaError_t launch_direct(const Geom &g, const Frames &f, int npairs, const Out 
     if (oo.ssd) oo.ssd += off;
     if (oo.score) oo.score += off;
     dim3 grid((g.W + kTX - 1) / kTX, (rows_px + kTY - 1) / kTY, n);
-    if (g.B == 16) direct_search_kernel<16><<<grid, kThreads, 0, s>>>(g, ff, oo);
-    else direct_search_kernel<8><<<grid, kThreads, 0, s>>>(g, ff, oo);
+    if (g.R == 0) {
+      if (g.B == 16) direct_search_kernel<16, true><<<grid, kThreads, 0, s>>>(g, ff, oo);
+      else direct_search_kernel<8, true><<<grid, kThreads, 0, s>>>(g, ff, oo);
+    } else {
+      if (g.B == 16) direct_search_kernel<16, false><<<grid, kThreads, 0, s>>>(g, ff, oo);
+      else direct_search_kernel<8, false><<<grid, kThreads, 0, s>>>(g, ff, oo);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     done += n;

@@ -1,5 +1,6 @@
 """Randomised parity fuzz on the GPU: random geometries / spans / frame contents, AUTO kernel (and the
-forced formulations) against the oracle.  usage: python tools/fuzz_parity.py [n_cases] [seed]"""
+forced formulations) against the oracle.
+usage: python tools/fuzz_parity.py [n_cases] [seed] [mode: mse | ssim | fast | all]"""
 import os
 import sys
 
@@ -15,6 +16,7 @@ from oracle_binding import Oracle  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    mode_arg = sys.argv[3] if len(sys.argv) > 3 else "mse"
     rng = np.random.Generator(np.random.PCG64(seed))
     orc = Oracle()
     bad = 0
@@ -28,7 +30,8 @@ def main():
         if rng.random() < 0.3:
             H = (H // B) * B + (B // 2 if rng.random() < 0.5 else 0)
         H = max(H, B)
-        kind = int(rng.integers(0, 5))
+        mode = mode_arg if mode_arg != "all" else str(rng.choice(["mse", "ssim", "fast"]))
+        kind = int(rng.integers(0, 6 if mode == "ssim" else 5))
         if kind == 0:
             cur, ref = me.random_pair(W, H, int(rng.integers(1 << 30)))
         elif kind == 1:
@@ -38,15 +41,28 @@ def main():
             cur, ref = me.constant_pair(W, H, int(rng.integers(0, 256)))
         elif kind == 3:
             cur, ref = me.checker_pair(W, H, int(rng.integers(1, 5)))
-        else:
+        elif kind == 4:
             cur, ref = me.far_pair(W, H, int(rng.integers(1 << 30)))
+        else:
+            cur, ref = me.inverted_pair(W, H, seed=int(rng.integers(1 << 30)), period=float(rng.uniform(5, 40)))
         form = str(rng.choice(["", "", "2", "1", "0"]))
         if form:
             os.environ["ME_B200_FORM"] = form
         else:
             os.environ.pop("ME_B200_FORM", None)
-        exp = orc.search(cur, ref, B, R)
-        with me.Estimator(W, H, B, R) as est:
+        if mode == "ssim":
+            if B == 32 and R > 16:
+                R = 16          # keep the CPU side of the fuzz short
+            exp = orc.search_ssim(cur, ref, B, R)
+            kw = dict(cost=me.ME_COST_SSIM, kernel=int(rng.choice([me.ME_KERNEL_AUTO, me.ME_KERNEL_AUTO, me.ME_KERNEL_GENERIC])))
+        elif mode == "fast":
+            algo = int(rng.integers(1, 3))
+            exp, _ = orc.search_fast(cur, ref, B, R, algo)
+            kw = dict(search=algo)
+        else:
+            exp = orc.search(cur, ref, B, R)
+            kw = {}
+        with me.Estimator(W, H, B, R, **kw) as est:
             out = est.search_u8(cur, ref)
             kern = est.kernel_in_use
         ok = (np.array_equal(out["mvx"][0], exp["mvx"]) and np.array_equal(out["mvy"][0], exp["mvy"]) and
@@ -54,8 +70,8 @@ def main():
               np.array_equal(out["score"][0].view(np.uint32), exp["score"].view(np.uint32)))
         if not ok:
             bad += 1
-            print(f"MISMATCH case {i}: W={W} H={H} B={B} R={R} kind={kind} form={form!r} kernel={kern}", flush=True)
-    print(f"fuzz: {n} cases, {bad} mismatches (seed {seed})")
+            print(f"MISMATCH case {i}: mode={mode} W={W} H={H} B={B} R={R} kind={kind} form={form!r} kernel={kern} {kw}", flush=True)
+    print(f"fuzz[{mode_arg}]: {n} cases, {bad} mismatches (seed {seed})")
     sys.exit(1 if bad else 0)
 
 
