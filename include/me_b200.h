@@ -183,6 +183,43 @@ int me_b200_search_device_band(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
                                int32_t *d_mvx, int32_t *d_mvy, uint32_t *d_ssd, float *d_score,
                                void *stream);
 
+/* ---- band sharding without a collective: peer-mapped fields over NVLink ---------------
+ * One process per GPU.  Every rank allocates its copy of the field with me_b200_device_alloc,
+ * exports it (CUDA IPC) and opens the copies of its peers; me_b200_search_device_band_peers
+ * then searches the rank's block rows and stores every block's result into the local field AND
+ * into each peer field -- from inside the search kernel where the tuned kernel runs, with a small
+ * store kernel for rows another kernel produced.  me_b200_peer_barrier is a device-side barrier
+ * between the GPUs (flags in the peer-mapped memory), enqueued on the same stream: when it has
+ * passed on a rank, every peer's band has landed in that rank's field.  Replaces the
+ * all_gather that followed me_b200_search_device_band. */
+#define ME_B200_MAX_PEERS        8
+#define ME_B200_IPC_HANDLE_BYTES 64
+typedef struct me_b200_field {
+  int32_t *mvx;
+  int32_t *mvy;
+  uint32_t *ssd;
+  float *score; /* any member may be NULL */
+} me_b200_field;
+/* zero-filled device memory on ctx's device (cudaMalloc, so it can be exported); NULL on failure */
+void *me_b200_device_alloc(me_b200_ctx *ctx, size_t bytes);
+void  me_b200_device_free(me_b200_ctx *ctx, void *d_ptr);
+int   me_b200_ipc_export(me_b200_ctx *ctx, void *d_ptr, unsigned char handle[ME_B200_IPC_HANDLE_BYTES]);
+int   me_b200_ipc_open(me_b200_ctx *ctx, const unsigned char handle[ME_B200_IPC_HANDLE_BYTES], void **d_ptr);
+int   me_b200_ipc_close(me_b200_ctx *ctx, void *d_ptr);
+/* npeers = number of OTHER GPUs (0..ME_B200_MAX_PEERS-1); peers[i] = field of the i-th of them. */
+int me_b200_search_device_band_peers(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                                     size_t pitch, size_t pair_stride, int npairs,
+                                     int by_begin, int by_end,
+                                     const me_b200_field *local, const me_b200_field *peers, int npeers,
+                                     void *stream);
+/* flags[q] = device pointer to rank q's flag array (>= nranks uint32, zero-initialised; flags[my_rank]
+ * is this rank's own array, the others are peer-mapped).  epoch must grow by one per barrier.
+ * Asynchronous on `stream`; gives up after timeout_ms (see me_b200_peer_barrier_timed_out). */
+int me_b200_peer_barrier(me_b200_ctx *ctx, uint32_t *const *flags, int nranks, int my_rank,
+                         uint32_t epoch, int timeout_ms, void *stream);
+/* synchronises the device; *timed_out = 1 if any barrier of this context gave up since the last call */
+int me_b200_peer_barrier_timed_out(me_b200_ctx *ctx, int *timed_out);
+
 /* ---- post-search stage on device ------------------------
  * replaces: main.c:160-168 (motionCompensatedFrame + 2x frameDiff, utils.c:94-134).
  * d_out5: 5 stacked W x H u8 planes (ref, cur, mc, |ref-cur|, |mc-cur|), stride W.

@@ -35,6 +35,7 @@ struct me_b200_ctx {
   int cost = ME_COST_MSE;          // me_b200_set_cost
   int search = ME_SEARCH_FULL;     // me_b200_set_search
   unsigned long long *d_evals = nullptr;  // fast search: candidate evaluations so far
+  int *d_peer_status = nullptr;           // peer barrier: 1 after a time-out
   char err[256] = {0};
   // scratch for the int-frame drop-in path
   uint8_t *h_cur = nullptr, *h_ref = nullptr;  // pinned, W*H each
@@ -303,6 +304,7 @@ void me_b200_destroy(me_b200_ctx *ctx) {
     }
     if (ctx->plan) me::tiled_plan_destroy(ctx->plan);
     cudaFree(ctx->d_evals);
+    cudaFree(ctx->d_peer_status);
     cudaFreeHost(ctx->h_cur);
     cudaFreeHost(ctx->h_ref);
     cudaFreeHost(ctx->h_mvx);
@@ -526,6 +528,122 @@ int me_b200_search_device_band(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
   me::Frames f{d_cur, d_ref, pitch, pair_stride};
   me::Out o{d_mvx, d_mvy, d_ssd, d_score};
   return run_search(ctx, f, npairs, by_begin, by_end, o, (cudaStream_t)stream);
+}
+
+// ---- band sharding over peer-mapped memory ------------------------------------------------
+
+void *me_b200_device_alloc(me_b200_ctx *ctx, size_t bytes) {
+  if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess || cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(p);
+    return nullptr;
+  }
+  cudaDeviceSynchronize();
+  return p;
+}
+
+void me_b200_device_free(me_b200_ctx *ctx, void *d_ptr) {
+  if (ctx && d_ptr && cudaSetDevice(ctx->device) == cudaSuccess) cudaFree(d_ptr);
+}
+
+int me_b200_ipc_export(me_b200_ctx *ctx, void *d_ptr, unsigned char handle[ME_B200_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == ME_B200_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!ctx || !d_ptr || !handle) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  ME_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, sizeof h);
+  return ME_OK;
+}
+
+int me_b200_ipc_open(me_b200_ctx *ctx, const unsigned char handle[ME_B200_IPC_HANDLE_BYTES], void **d_ptr) {
+  if (!ctx || !handle || !d_ptr) return ME_ERR_INVALID_ARG;
+  *d_ptr = nullptr;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  ME_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ME_OK;
+}
+
+int me_b200_ipc_close(me_b200_ctx *ctx, void *d_ptr) {
+  if (!ctx || !d_ptr) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  ME_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+  return ME_OK;
+}
+
+int me_b200_search_device_band_peers(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                                     size_t pitch, size_t pair_stride, int npairs, int by_begin, int by_end,
+                                     const me_b200_field *local, const me_b200_field *peers, int npeers,
+                                     void *stream) {
+  if (!ctx || !d_cur || !d_ref || !local || npairs < 1) return ME_ERR_INVALID_ARG;
+  if (npeers < 0 || npeers >= ME_B200_MAX_PEERS || (npeers > 0 && !peers)) return ME_ERR_INVALID_ARG;
+  if (pitch < (size_t)ctx->g.W) return ME_ERR_INVALID_ARG;
+  if (npairs > 1 && pair_stride < pitch * (size_t)ctx->g.H) return ME_ERR_INVALID_ARG;
+  if (by_begin < 0 || by_end > ctx->g.nby || by_begin > by_end) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  me::Frames f{d_cur, d_ref, pitch, pair_stride};
+  me::Out o{local->mvx, local->mvy, local->ssd, local->score};
+  me::Out po[ME_B200_MAX_PEERS];
+  for (int i = 0; i < npeers; i++) po[i] = me::Out{peers[i].mvx, peers[i].mvy, peers[i].ssd, peers[i].score};
+  // the tuned kernel stores into the peers itself; whatever block rows it did not cover (other
+  // kernels, partial bottom rows) are stored by the small peer kernel afterwards
+  if (ctx->plan) me::tiled_plan_set_peers(ctx->plan, po, npeers);
+  rc = run_search(ctx, f, npairs, by_begin, by_end, o, (cudaStream_t)stream);
+  int fb = by_begin, fe = by_begin;
+  if (ctx->plan) {
+    me::tiled_plan_fused_rows(ctx->plan, &fb, &fe);
+    me::tiled_plan_set_peers(ctx->plan, nullptr, 0);
+  }
+  if (rc) return rc;
+  if (npeers == 0) return ME_OK;
+  if (fe <= fb) fb = fe = by_begin;
+  cudaError_t e = me::launch_peer_scatter(ctx->g, npairs, by_begin, fb, o, po, npeers, (cudaStream_t)stream);
+  if (e == cudaSuccess)
+    e = me::launch_peer_scatter(ctx->g, npairs, fe, by_end, o, po, npeers, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_peer_scatter");
+  if (fb > by_begin) ctx->launches++;
+  if (by_end > fe) ctx->launches++;
+  return ME_OK;
+}
+
+int me_b200_peer_barrier(me_b200_ctx *ctx, uint32_t *const *flags, int nranks, int my_rank, uint32_t epoch,
+                         int timeout_ms, void *stream) {
+  if (!ctx || !flags || nranks < 1 || nranks > ME_B200_MAX_PEERS || my_rank < 0 || my_rank >= nranks)
+    return ME_ERR_INVALID_ARG;
+  for (int i = 0; i < nranks; i++)
+    if (!flags[i]) return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!ctx->d_peer_status) {
+    ME_CUDA(ctx, cudaMalloc((void **)&ctx->d_peer_status, 256));
+    ME_CUDA(ctx, cudaMemset(ctx->d_peer_status, 0, 256));
+  }
+  const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 1000) * 1000000ull;
+  cudaError_t e = me::launch_peer_barrier(flags, nranks, my_rank, epoch, ns, ctx->d_peer_status,
+                                          (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_peer_barrier");
+  ctx->launches++;
+  return ME_OK;
+}
+
+int me_b200_peer_barrier_timed_out(me_b200_ctx *ctx, int *timed_out) {
+  if (!ctx || !timed_out) return ME_ERR_INVALID_ARG;
+  *timed_out = 0;
+  if (!ctx->d_peer_status) return ME_OK;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  ME_CUDA(ctx, cudaDeviceSynchronize());
+  ME_CUDA(ctx, cudaMemcpy(timed_out, ctx->d_peer_status, sizeof(int), cudaMemcpyDeviceToHost));
+  ME_CUDA(ctx, cudaMemset(ctx->d_peer_status, 0, sizeof(int)));
+  return ME_OK;
 }
 
 int me_b200_search_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref, size_t pitch,

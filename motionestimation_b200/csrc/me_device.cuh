@@ -44,6 +44,10 @@ struct TiledPlan;  // opaque: tensor maps + launch shape
 cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int max_pairs);
 void tiled_plan_destroy(TiledPlan *plan);
 unsigned long long tiled_plan_launches(const TiledPlan *plan);  // kernels launched so far
+// Band sharding over NVLink: the next launch_tiled also stores every block's result into `peers`
+// (output arrays in peer-mapped memory); tiled_plan_fused_rows reports the block rows it covered.
+int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers);
+void tiled_plan_fused_rows(const TiledPlan *plan, int *begin, int *end);
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err_text);
 
@@ -58,6 +62,13 @@ cudaError_t launch_ssim(const Geom &g, const Frames &f, int npairs, const Out &o
 int tss_first_step(int R);
 cudaError_t launch_fast(const Geom &g, const Frames &f, int npairs, const Out &o, int algo,
                         unsigned long long *evals, cudaStream_t s);
+
+// Peer plumbing (me_peer.cu): copy block rows [by_begin, by_end) of a field into the peers'
+// fields with plain stores over NVLink, and a device-side flag barrier between the GPUs.
+cudaError_t launch_peer_scatter(const Geom &g, int npairs, int by_begin, int by_end, const Out &local,
+                                const Out *peers, int npeers, cudaStream_t s);
+cudaError_t launch_peer_barrier(uint32_t *const *flags, int npeers, int my_rank, uint32_t epoch,
+                                unsigned long long timeout_ns, int *d_status, cudaStream_t s);
 
 cudaError_t launch_postprocess(const Geom &g, const uint8_t *cur, const uint8_t *ref, size_t pitch,
                                const int32_t *mvx, const int32_t *mvy, uint8_t *out5,

@@ -75,6 +75,7 @@ constexpr int kMaxStages = 4;
 constexpr int kWinPitch = 256;  // window row pitch in shared memory = TMA box width (the maximum);
                                 // a compile-time pitch turns every row offset into an LDS immediate
 constexpr uint32_t kNoKey = 0xffffffffu;
+constexpr int kMaxPeerOuts = 7;  // other GPUs of one NVSwitch domain
 
 struct TiledParams {
   int W, H, B, R;
@@ -100,6 +101,10 @@ struct TiledParams {
   unsigned int inv_ndx;    // ceil(2^32 / (2R+1)): exact quotient by multiply-high for n < 2^16
   unsigned int *next_item; // global work counter of this launch (zeroed on the stream before it)
   Out out;
+  // band sharding over NVLink: every published block is also stored into the output arrays of the
+  // peer GPUs (peer-mapped memory), so no collective follows the search
+  int npeer;
+  Out peer[kMaxPeerOuts];
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -176,7 +181,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int WORDS, int BH, int NSUB, int FORM, bool PW>
+template <int WORDS, int BH, int NSUB, int FORM, bool PW, bool PEER>
 __global__ void __launch_bounds__(kThreads, 1)
 tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
                     const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_sh,
@@ -500,6 +505,18 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           if (p.out.ssd) p.out.ssd[oi] = ssd;
           const int bw = min(BW, p.W - bx * BW);
           if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(bw * I.h));  // main.c:27
+          if constexpr (PEER) {
+            const float score = __fdiv_rn((float)ssd, (float)(bw * I.h));
+            // same four values into every peer's copy of the field (a separate instantiation: the
+            // plain kernel's code is untouched -- its placement is worth more than 1 %)
+            for (int q = 0; q < p.npeer; q++) {
+              const Out &po = p.peer[q];
+              if (po.mvx) po.mvx[oi] = (int)(uint32_t)key - p.R;
+              if (po.mvy) po.mvy[oi] = (int)(k32 & 0xff) - p.R;
+              if (po.ssd) po.ssd[oi] = ssd;
+              if (po.score) po.score[oi] = score;
+            }
+          }
         }
       }
       __syncwarp();
@@ -610,6 +627,12 @@ struct TiledPlan {
   int ns_override = 0;
   unsigned long long kernels_launched = 0;  // every kernel this plan has launched (search + pre-pass)
   bool form_env_forced = false;  // ME_B200_FORM=2: use the table even for tiny launches (tests)
+  // peer outputs of the NEXT launch (band sharding over NVLink), and the block rows that launch
+  // actually wrote to the peers from inside the search kernel ([fused_begin, fused_end))
+  Out peer[kMaxPeerOuts];
+  int npeer = 0;
+  int fused_begin = 0, fused_end = 0;
+  bool fused_launch = false;  // the last search kernel launched was a peer-storing instantiation
   int form = 2;  // 2: energy table when possible, else 1 (default); 1: on-the-fly energies;
                  // 0: |a-b|^2 -- env ME_B200_FORM selects 0/1 for A/B measurements
 };
@@ -670,6 +693,20 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
 }
 
 void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
+
+int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers) {
+  if (!plan || npeers < 0 || npeers > kMaxPeerOuts) return -1;
+  for (int i = 0; i < npeers; i++) plan->peer[i] = peers[i];
+  plan->npeer = npeers;
+  plan->fused_begin = plan->fused_end = 0;
+  plan->fused_launch = false;
+  return 0;
+}
+
+void tiled_plan_fused_rows(const TiledPlan *plan, int *begin, int *end) {
+  *begin = plan ? plan->fused_begin : 0;
+  *end = plan ? plan->fused_end : 0;
+}
 unsigned long long tiled_plan_launches(const TiledPlan *plan) { return plan ? plan->kernels_launched : 0; }
 
 namespace {
@@ -748,6 +785,12 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.stages = (plan->max_smem - static_smem) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.out = o;
+  // peer stores from inside the kernel exist for the two default formulations on full-width
+  // frames; other launches leave the peers to the caller's store kernel
+  constexpr bool kPeerVariant = FORM >= 1 && !PW;
+  const bool peer = kPeerVariant && plan->npeer > 0;
+  p.npeer = peer ? plan->npeer : 0;
+  for (int q = 0; q < p.npeer; q++) p.peer[q] = plan->peer[q];
   p.inv_ndx = (unsigned int)((0x100000000ull + (unsigned)(2 * g.R + 1) - 1) / (unsigned)(2 * g.R + 1));
   {
     const char *sk = getenv("ME_B200_SKEW");
@@ -847,7 +890,10 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   if (getenv("ME_B200_VERBOSE"))
     fprintf(stderr, "[me_b200] tiled<%d,%d,%d,form %d> ns=%d parts=%d items=%d stages=%d stage=%d B smem=%d B s_pitch=%d\n",
             WORDS, BH, NSUB, FORM, p.ns, p.parts_target, p.total_items, p.stages, p.stage_bytes, smem, p.s_pitch);
-  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW>;
+  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, false>;
+  if constexpr (kPeerVariant) {
+    if (peer) kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, true>;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     *err = "cudaFuncSetAttribute(tiled)";
@@ -860,6 +906,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   plan->kernels_launched++;
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
+  if (e == cudaSuccess && peer) plan->fused_launch = true;
   if (d_s) cudaFreeAsync(d_s, s);
   cudaFreeAsync(d_ctr, s);
   return e;
@@ -914,6 +961,10 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
       else e = launch_shape<8, 8, 4, 0>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
     }
     if (e != cudaSuccess) return e;
+    if (plan->npeer > 0 && plan->fused_launch) {
+      plan->fused_begin = r0;
+      plan->fused_end = t1;
+    }
   }
   if (r1 > tiled_rows) {
     Geom gb = g;

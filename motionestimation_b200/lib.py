@@ -27,6 +27,8 @@ ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT = 0, 1, 2, 
 ME_COST_MSE, ME_COST_SSIM = 0, 1
 ME_SEARCH_FULL, ME_SEARCH_THREE_STEP, ME_SEARCH_DIAMOND = 0, 1, 2
 ME_B200_MAX_SLOTS = 4
+ME_B200_MAX_PEERS = 8
+ME_B200_IPC_HANDLE_BYTES = 64
 
 PEAK_NAMES = ["IDP4A", "VABSDIFF4", "SSD_PAIR", "IADD3", "LOP3", "IMAD", "VIMNMX",
               "SSD_PAIR_LDS", "IDP4A_IADD3", "LOOP_REPLICA"]
@@ -43,6 +45,11 @@ class Block(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "idx_x", "idx_y", "top_left_x", "top_left_y", "bottom_right_x", "bottom_right_y",
         "width", "height", "is_best_match_found", "motion_vectorX", "motion_vectorY")]
+
+
+class Field(C.Structure):
+    """``me_b200_field``: device pointers of one copy of the motion field (any may be NULL)."""
+    _fields_ = [("mvx", C.c_void_p), ("mvy", C.c_void_p), ("ssd", C.c_void_p), ("score", C.c_void_p)]
 
 
 class PredictionFrame(C.Structure):
@@ -110,6 +117,15 @@ def load_library() -> C.CDLL:
                                             i32p, i32p, u32p, f32p, vp]),
         "me_b200_search_device_band": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int,
                                                  C.c_int, C.c_int, i32p, i32p, u32p, f32p, vp]),
+        "me_b200_device_alloc": (vp, [vp, C.c_size_t]),
+        "me_b200_device_free": (None, [vp, vp]),
+        "me_b200_ipc_export": (C.c_int, [vp, vp, C.c_char_p]),
+        "me_b200_ipc_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "me_b200_ipc_close": (C.c_int, [vp, vp]),
+        "me_b200_search_device_band_peers": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                                       C.c_int, C.POINTER(Field), C.POINTER(Field), C.c_int, vp]),
+        "me_b200_peer_barrier": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_uint32, C.c_int, vp]),
+        "me_b200_peer_barrier_timed_out": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "me_b200_postprocess_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, i32p, i32p, u8p, vp, vp, vp]),
         "me_b200_int_peak": (C.c_double, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         # host layer (include/me_common.h)
@@ -291,6 +307,50 @@ class Estimator:
         self._check(self._lib.me_b200_search_device_band(
             self._h, p(d_cur), p(d_ref), pitch, pair_stride, npairs, by_begin, by_end,
             p(d_mvx), p(d_mvy), p(d_ssd), p(d_score), stream or None), "me_b200_search_device_band")
+
+    # -- band sharding over peer-mapped fields (one process per GPU, CUDA IPC over NVLink) -------
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._lib.me_b200_device_alloc(self._h, nbytes)
+        if not p:
+            raise MeError(ME_ERR_NOMEM, "me_b200_device_alloc")
+        return int(p)
+
+    def device_free(self, ptr: int):
+        self._lib.me_b200_device_free(self._h, ptr)
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(ME_B200_IPC_HANDLE_BYTES)
+        self._check(self._lib.me_b200_ipc_export(self._h, ptr, buf), "me_b200_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.me_b200_ipc_open(self._h, handle, C.byref(p)), "me_b200_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.me_b200_ipc_close(self._h, ptr), "me_b200_ipc_close")
+
+    def search_device_band_peers(self, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, by_begin: int,
+                                 by_end: int, local: "Field", peers, stream: int = 0):
+        """Search block rows [by_begin, by_end) and store the results into `local` and every field of
+        `peers` (peer-mapped device memory)."""
+        def p(x):
+            return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+        arr = (Field * max(1, len(peers)))(*peers)
+        self._check(self._lib.me_b200_search_device_band_peers(
+            self._h, p(d_cur), p(d_ref), pitch, pair_stride, npairs, by_begin, by_end, C.byref(local), arr,
+            len(peers), stream or None), "me_b200_search_device_band_peers")
+
+    def peer_barrier(self, flag_ptrs, my_rank: int, epoch: int, timeout_ms: int = 2000, stream: int = 0):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._check(self._lib.me_b200_peer_barrier(self._h, arr, len(flag_ptrs), my_rank, epoch, timeout_ms,
+                                                   stream or None), "me_b200_peer_barrier")
+
+    def peer_barrier_timed_out(self) -> bool:
+        v = C.c_int(0)
+        self._check(self._lib.me_b200_peer_barrier_timed_out(self._h, C.byref(v)), "me_b200_peer_barrier_timed_out")
+        return bool(v.value)
 
     def postprocess_device(self, d_cur, d_ref, pitch: int, d_mvx, d_mvy, d_out5, d_sq_err=None,
                            d_max=None, stream: int = 0):

@@ -12,8 +12,12 @@ frame pairs -- are independent, which gives two shardings, one process per GPU:
   frame, so there is no halo exchange -- and ONE collective at the end gathers the
   per-band slices of the field (``all_gather`` over NCCL on GPUs; gloo in CPU tests).
 
-torch.distributed is plumbing here: rendezvous and the gather.  The search is
-always the CUDA library.
+  :class:`PeerField` + :func:`search_banded_peer` do the same WITHOUT a collective: every rank
+  maps the field buffers of its peers (CUDA IPC over NVLink/NVSwitch) and the search kernel
+  stores each finished block into all copies; a device-side flag barrier replaces the gather.
+
+torch.distributed is plumbing here: rendezvous, the exchange of the IPC handles and the gather.
+The search is always the CUDA library.
 """
 from __future__ import annotations
 
@@ -76,6 +80,18 @@ def all_band_rows(nby: int, world: int, weights: Optional[Sequence[float]] = Non
     return [band_rows(nby, world, r, weights) for r in range(world)]
 
 
+_SPANS_CACHE = {}
+
+
+def balanced_spans(est, world: int, balance: bool = True) -> List[Tuple[int, int]]:
+    """Bands of all ranks for an estimator's geometry (cached: this sits on the launch path)."""
+    key = (est.width, est.height, est.blk_dim, est.extra_span, world, balance)
+    if key not in _SPANS_CACHE:
+        weights = row_costs(est.width, est.height, est.blk_dim, est.extra_span) if balance else None
+        _SPANS_CACHE[key] = all_band_rows(est.blocks_y, world, weights)
+    return _SPANS_CACHE[key]
+
+
 def gather_bands(local: "torch.Tensor", rows: Tuple[int, int], nby: int, nbx: int, group=None,
                  spans: Optional[List[Tuple[int, int]]] = None):
     """All-gather the per-band slices of a field with ONE collective.
@@ -122,8 +138,7 @@ def search_banded(est, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, 
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    weights = row_costs(est.width, est.height, est.blk_dim, est.extra_span) if balance else None
-    spans = all_band_rows(est.blocks_y, world, weights)
+    spans = balanced_spans(est, world, balance)
     b0, b1 = spans[rank]
     nb, nbx = est.num_blocks, est.blocks_x
     packed = torch.zeros((4, npairs, nb), dtype=torch.int32, device=d_cur.device)  # mvx, mvy, ssd, score bits
@@ -131,3 +146,84 @@ def search_banded(est, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, 
                       stream, b0, b1)
     full = gather_bands(packed[:, :, b0 * nbx: b1 * nbx], (b0, b1), est.blocks_y, nbx, group, spans)
     return {"mvx": full[0], "mvy": full[1], "ssd": full[2], "score": full[3].view(torch.float32)}
+
+
+class _RawCuda:
+    """Minimal ``__cuda_array_interface__`` view of library-owned device memory (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+class PeerField:
+    """The motion field of a batch, one copy per rank, every copy mapped into every rank.
+
+    Layout of a copy: int32 mvx | int32 mvy | uint32 ssd | float score, each ``npairs * num_blocks``
+    entries, then ``ME_B200_MAX_PEERS`` uint32 barrier flags.  The memory comes from
+    ``me_b200_device_alloc`` (exportable), the handles travel through ``all_gather_object``."""
+
+    def __init__(self, est, npairs: int, group=None):
+        import torch.distributed as dist
+        from .lib import Field, ME_B200_MAX_PEERS
+        self.est, self.npairs, self.group = est, npairs, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > ME_B200_MAX_PEERS:
+            raise ValueError("at most %d ranks" % ME_B200_MAX_PEERS)
+        self.entries = npairs * est.num_blocks
+        self.nbytes = 4 * 4 * self.entries + 256
+        self.base = est.device_alloc(self.nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, est.ipc_export(self.base), group=group)
+        self.bases, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.bases.append(self.base)
+            else:
+                p = est.ipc_open(h)
+                self._opened.append(p)
+                self.bases.append(p)
+        a = 4 * self.entries
+        self.fields = [Field(b, b + a, b + 2 * a, b + 3 * a) for b in self.bases]
+        self.flag_ptrs = [b + 4 * a for b in self.bases]
+        self.peer_fields = [self.fields[r] for r in range(self.world) if r != self.rank]
+        self._tensors = None
+        self.epoch = 0
+        dist.barrier(group=group)    # every rank has opened every copy before anyone writes
+
+    def tensors(self):
+        """This rank's copy as torch tensors (views, no copy)."""
+        import torch
+        if self._tensors is None:
+            shape = (self.npairs, self.est.num_blocks)
+            a = 4 * self.entries
+            t = [torch.as_tensor(_RawCuda(self.base + i * a, shape, "<i4"), device="cuda") for i in range(3)]
+            sc = torch.as_tensor(_RawCuda(self.base + 3 * a, shape, "<f4"), device="cuda")
+            self._tensors = {"mvx": t[0], "mvy": t[1], "ssd": t[2], "score": sc}
+        return self._tensors
+
+    def close(self):
+        import torch.distributed as dist
+        if self.base:
+            self._tensors = None
+            dist.barrier(group=self.group)   # nobody closes while a peer may still write
+            for p in self._opened:
+                self.est.ipc_close(p)
+            self._opened = []
+            self.est.device_free(self.base)
+            self.base = 0
+
+
+def search_banded_peer(est, field: PeerField, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int,
+                       stream: int = 0, balance: bool = True):
+    """As :func:`search_banded`, but with no collective: the rank's band is stored into every
+    rank's copy of `field` by the search itself, then one device-side barrier (flags in the
+    peer-mapped memory) tells each rank that all bands have landed.  Returns views of the local copy."""
+    spans = balanced_spans(est, field.world, balance)
+    b0, b1 = spans[field.rank]
+    peers = field.peer_fields
+    est.search_device_band_peers(d_cur, d_ref, pitch, pair_stride, npairs, b0, b1, field.fields[field.rank],
+                                 peers, stream)
+    field.epoch += 1
+    est.peer_barrier(field.flag_ptrs, field.rank, field.epoch, 2000, stream)
+    return field.tensors()

@@ -76,6 +76,13 @@ def test_argument_validation_needs_no_gpu():
     assert lib.me_b200_num_blocks(None) == 0
     assert lib.me_b200_strerror(me.ME_ERR_NO_DEVICE).decode().startswith("no usable CUDA device")
     lib.me_b200_destroy(None)  # no-op
+    # peer-field entry points
+    assert lib.me_b200_device_alloc(None, 16) is None
+    assert lib.me_b200_peer_barrier(None, None, 2, 0, 1, 10, None) == me.ME_ERR_INVALID_ARG
+    assert lib.me_b200_search_device_band_peers(None, None, None, 0, 0, 1, 0, 0, None, None, 0, None) == \
+        me.ME_ERR_INVALID_ARG
+    assert lib.me_b200_ipc_export(None, None, None) == me.ME_ERR_INVALID_ARG
+    assert C.sizeof(me.Field) == 32
 
 
 @pytest.mark.skipif(me.device_count() > 0, reason="this test is about machines without a GPU")

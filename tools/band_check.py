@@ -1,6 +1,8 @@
 """torchrun --nproc-per-node N tools/band_check.py : one 4K frame pair split by block-row
-bands over N GPUs, field gathered with one NCCL all_gather per array, compared on every rank
-with the unsharded search.  Prints the device time of the banded search (max over ranks)."""
+bands over N GPUs; the field is completed (a) with one NCCL all_gather of the packed arrays and
+(b) with no collective at all: peer-mapped fields, the search kernel stores into every rank's copy,
+one device-side flag barrier.  Both are compared on every rank with the unsharded search.  Prints
+the device times (max over ranks)."""
 import os
 import sys
 
@@ -38,24 +40,56 @@ def main():
             res = sharding.search_banded(est, cur, ref, W, W * H, 1)
         torch.cuda.synchronize()
         dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = sharding.search_banded(est, cur, ref, W, W * H, 1)
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        tn = []
+        for _ in range(5):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = sharding.search_banded(est, cur, ref, W, W * H, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            tn.append(e0.elapsed_time(e1))
+        t = torch.tensor([sorted(tn)[len(tn) // 2]], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ok = (np.array_equal(res["mvx"].cpu().numpy(), full["mvx"]) and
               np.array_equal(res["mvy"].cpu().numpy(), full["mvy"]) and
               np.array_equal(res["ssd"].cpu().numpy().view(np.uint32), full["ssd"]) and
               np.array_equal(res["score"].cpu().numpy().view(np.uint32), full["score"].view(np.uint32)))
-        flag = torch.tensor([1 if ok else 0], device="cuda")
+        # (b) peer-mapped fields: no collective
+        field = sharding.PeerField(est, 1)
+        for _ in range(3):
+            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        tp = []
+        for _ in range(5):
+            dist.barrier()
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1)
+            p1.record()
+            torch.cuda.synchronize()
+            tp.append(p0.elapsed_time(p1))
+        tpeer = torch.tensor([sorted(tp)[len(tp) // 2]], device="cuda")
+        dist.all_reduce(tpeer, op=dist.ReduceOp.MAX)
+        timed_out = est.peer_barrier_timed_out()
+        okp = (not timed_out and np.array_equal(resp["mvx"].cpu().numpy(), full["mvx"]) and
+               np.array_equal(resp["mvy"].cpu().numpy(), full["mvy"]) and
+               np.array_equal(resp["ssd"].cpu().numpy().view(np.uint32), full["ssd"]) and
+               np.array_equal(resp["score"].cpu().numpy().view(np.uint32), full["score"].view(np.uint32)))
+        del resp
+        torch.cuda.synchronize()
+        field.close()
+        flag = torch.tensor([1 if ok else 0, 1 if okp else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f"band sharding x{world}: 4K 16x16 +-{R} one pair, banded search + gather {t.item():.3f} ms "
-                  f"(max over ranks) vs {t_single:.3f} ms unsharded on one GPU, identical on all ranks: "
-                  f"{bool(flag.item())}", flush=True)
-        assert ok
+            print(f"band sharding x{world}: 4K 16x16 +-{R} one pair: unsharded {t_single:.3f} ms | banded search + "
+                  f"NCCL all_gather {t.item():.3f} ms, identical on all ranks: {bool(flag[0].item())} | banded search "
+                  f"storing into peer-mapped fields + device flag barrier {tpeer.item():.3f} ms, identical on all "
+                  f"ranks: {bool(flag[1].item())} (max over ranks)", flush=True)
+        assert ok and okp
     dist.destroy_process_group()
 
 
