@@ -187,59 +187,98 @@ ssim_generic_kernel(Geom g, Frames f, Out o, int bx_begin, int bx_count, int sme
 }
 
 // ------------------------------------------------------------------ statistics pre-pass
-// One thread per position (x, y) of the table = top-left corner of a BW x BH rectangle of the
-// reference frame; a CTA covers kSx x kSy positions.  The pixels it needs are staged as floats
-// (exact).  The pixel sum of ssim.c:3-11 is an exact integer: horizontal box sums are built
-// cooperatively, each position adds BH of them.  The variance (ssim.c:16-27) is the literal
-// raster-order float loop: LDS + FSUB + FMUL + FADD per pixel -- this is what the pre-pass costs
-// (1 KB of shared-memory reads and 768 dependent float operations per position).
+// {pixel sum, stddev} of every BW x BH rectangle of the reference frame (table entry per top-left
+// corner).  A CTA covers kSx x kSy positions and stages the pixels it needs as floats (exact).
+//   * pixel sum (ssim.c:3-11): an exact integer -- horizontal box sums are built cooperatively
+//     (one full sum + three one-pixel slides per group of four), each position adds BH of them;
+//   * variance (ssim.c:16-27): the literal raster-order float loop, FSUB + FMUL + FADD per pixel.
+//     A thread owns FOUR horizontally adjacent positions (x = 4j .. 4j+3): their rows overlap in
+//     BW - 1 of BW pixels, so one row costs (BW + 6) / 4 aligned LDS.128 for all four instead of
+//     4 * BW scalar loads -- 320 B of shared-memory traffic per position instead of 1 KB, which
+//     moves the kernel from the shared-memory roof to the FP32 roof (768 dependent-free float
+//     operations per 16x16 position).
 // Table entry = {pixel sum (int), stddev (float bits)}; mean = sum / (BW*BH) is exact to
 // recompute because BW*BH is a power of two.  Rectangles that leave the frame are not
 // candidates of any block: skipped.
-constexpr int kSx = 32, kSy = 8;
+constexpr int kSx = 128, kSy = 8;   // positions per CTA: 32 threads x 4 positions wide, 8 rows
+constexpr int kStatThreads = (kSx / 4) * kSy;
 
 template <int BW, int BH>
-__global__ void __launch_bounds__(kSx * kSy)
+__global__ void __launch_bounds__(kStatThreads)
 ssim_stats_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_stride, int W, int H, int y_lo,
                   int y_hi, int2 *__restrict__ table, size_t table_pair_stride) {
-  constexpr int TW = kSx + BW - 1, TH = kSy + BH - 1;
-  __shared__ float px[TH][TW];
-  __shared__ float hs[TH][kSx];
+  constexpr int NF4 = (BW + 6) / 4;                  // float4 loads per row for four positions
+  constexpr int TW = kSx + 4 * NF4 - 4, TH = kSy + BH - 1;
+  static_assert(TW % 4 == 0 && TW >= kSx + BW - 1, "tile width");
+  __shared__ __align__(16) float px[TH][TW];
+  __shared__ __align__(16) float hs[TH][kSx];
   const int tx0 = blockIdx.x * kSx, ty0 = y_lo + blockIdx.y * kSy;
   const uint8_t *src = ref + (size_t)blockIdx.z * pair_stride;
-  for (int i = threadIdx.x; i < TH * TW; i += kSx * kSy) {
+  for (int i = threadIdx.x; i < TH * TW; i += kStatThreads) {
     const int r = i / TW, c = i - r * TW;
     const int y = ty0 + r, x = tx0 + c;
     px[r][c] = (y < H && x < W) ? (float)src[(size_t)y * pitch + x] : 0.0f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < TH * kSx; i += kSx * kSy) {
-    const int r = i / kSx, c = i - r * kSx;
+  // horizontal box sums, four adjacent ones per step: integers <= 255*BW, exact in any order
+  for (int i = threadIdx.x; i < TH * (kSx / 4); i += kStatThreads) {
+    const int r = i / (kSx / 4), c4 = (i - r * (kSx / 4)) * 4;
+    float f[4 * NF4];
+#pragma unroll
+    for (int k = 0; k < NF4; k++) {
+      const float4 v = *reinterpret_cast<const float4 *>(&px[r][c4 + 4 * k]);
+      f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+    }
     float a = 0.0f;
 #pragma unroll
-    for (int k = 0; k < BW; k++) a += px[r][c + k];   // integers <= 255*BW: exact in any order
-    hs[r][c] = a;
+    for (int k = 0; k < BW; k++) a += f[k];
+    float4 o;
+    o.x = a;
+    a = a - f[0] + f[BW];     o.y = a;
+    a = a - f[1] + f[BW + 1]; o.z = a;
+    a = a - f[2] + f[BW + 2]; o.w = a;
+    *reinterpret_cast<float4 *>(&hs[r][c4]) = o;
   }
   __syncthreads();
-  const int lx = threadIdx.x % kSx, ly = threadIdx.x / kSx;
-  const int x = tx0 + lx, y = ty0 + ly;
-  if (x + BW > W || y + BH > H || y > y_hi) return;
+  const int lx4 = (threadIdx.x % (kSx / 4)) * 4, ly = threadIdx.x / (kSx / 4);
+  const int x = tx0 + lx4, y = ty0 + ly;
+  if (x + BW > W || y + BH > H || y > y_hi) return;  // (the first of the four positions decides the rest below)
   const float area = (float)(BW * BH);
-  float sum = 0.0f;                                  // ssim.c:5-11: integers < 2^24, exact
+  float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // ssim.c:5-11: integers < 2^24, exact
 #pragma unroll
-  for (int oy = 0; oy < BH; oy++) sum += hs[ly + oy][lx];
-  const float m = __fdiv_rn(sum, area);              // ssim.c:12
-  float vs = 0.0f;                                   // ssim.c:18-24, raster order
+  for (int oy = 0; oy < BH; oy++) {
+    const float4 v = *reinterpret_cast<const float4 *>(&hs[ly + oy][lx4]);
+    sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+  }
+  float m[4], vs[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    m[c] = __fdiv_rn(sum[c], area);                  // ssim.c:12
+    vs[c] = 0.0f;
+  }
 #pragma unroll 2
-  for (int oy = 0; oy < BH; oy++)
+  for (int oy = 0; oy < BH; oy++) {                  // ssim.c:18-24, raster order per position
+    float f[4 * NF4];
 #pragma unroll
-    for (int ox = 0; ox < BW; ox++) {
-      const float d = __fsub_rn(px[ly + oy][lx + ox], m);
-      vs = __fadd_rn(vs, __fmul_rn(d, d));
+    for (int k = 0; k < NF4; k++) {
+      const float4 v = *reinterpret_cast<const float4 *>(&px[ly + oy][lx4 + 4 * k]);
+      f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
     }
-  const float sd = __fsqrt_rn(__fdiv_rn(vs, area));  // ssim.c:25, :52
-  table[(size_t)blockIdx.z * table_pair_stride + (size_t)(y - y_lo) * W + x] =
-      make_int2((int)sum, (int)__float_as_uint(sd));
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int ox = 0; ox < BW; ox++) {
+        const float d = __fsub_rn(f[c + ox], m[c]);
+        vs[c] = __fadd_rn(vs[c], __fmul_rn(d, d));
+      }
+  }
+  int2 *dst = table + (size_t)blockIdx.z * table_pair_stride + (size_t)(y - y_lo) * W + x;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    if (x + c + BW <= W) {
+      const float sd = __fsqrt_rn(__fdiv_rn(vs[c], area));  // ssim.c:25, :52
+      dst[c] = make_int2((int)sum[c], (int)__float_as_uint(sd));
+    }
 }
 
 // Statistics of the CURRENT blocks (ssim.c:49,51,53) of the block rows of one launch: one thread
@@ -532,7 +571,7 @@ cudaError_t launch_ssim_tiled_pitch(const Geom &g, const Frames &f, int npairs, 
   for (int done = 0; done < npairs && e == cudaSuccess; done += 65535) {
     const int np = npairs - done > 65535 ? 65535 : npairs - done;
     dim3 sg((g.W - BW + 1 + kSx - 1) / kSx, (nrows + kSy - 1) / kSy, np);
-    ssim_stats_kernel<BW, BH><<<sg, kSx * kSy, 0, s>>>(f.ref + (size_t)done * ref_pair_stride, f.pitch,
+    ssim_stats_kernel<BW, BH><<<sg, kStatThreads, 0, s>>>(f.ref + (size_t)done * ref_pair_stride, f.pitch,
                                                        ref_pair_stride, g.W, g.H, y_lo, y_hi,
                                                        table + (size_t)done * p.table_pair_stride,
                                                        p.table_pair_stride);
