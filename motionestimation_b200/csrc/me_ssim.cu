@@ -39,6 +39,7 @@
 //                         feeds up to VB dot products); float epilogue per candidate.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "me_device.cuh"
 
@@ -392,11 +393,17 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
     const int dx_lo = max(0, p.R - x0), dx_hi = min(2 * p.R, p.W - BW - x0 + p.R);
     const int dy_lo = max(0, p.R - y0), dy_hi = min(2 * p.R, p.H - BH - y0 + p.R);
     const int ncx = dx_hi - dx_lo + 1, ncy = dy_hi - dy_lo + 1;
-    const int ngy = (ncy + VB - 1) / VB;
-    const int ntasks = ncx * ngy;
+    // full groups of VB vertically adjacent candidates first; the ncy % VB rows that are left are
+    // scored in groups of 4, 2 and 1 (same body) -- no lane ever scores a candidate that does not
+    // exist
+    // (a remainder of 5..7 rows is cheaper as one more group of VB with its missing rows masked:
+    // it shares a pass with the full groups instead of costing up to three thin passes)
+    const int ngy_full = ncy / VB, nrem = ncy - ngy_full * VB;
+    const bool tail_group = nrem >= 5;
+    const int ngy = ngy_full + (tail_group ? 1 : 0), nleft = tail_group ? 0 : nrem;
     // start with the group of rows that holds zero motion (dy = R): on real video the best scores
     // sit there, so the pruning threshold is high from the first tasks on
-    const int gy_first = (p.R - dy_lo) / VB;
+    const int gy_first = ngy > 0 ? min((p.R - dy_lo) / VB, ngy - 1) : 0;
 
     uint32_t cw[BH][WORDS];
 #pragma unroll
@@ -411,73 +418,101 @@ ssim_tiled_kernel(const __grid_constant__ SsimTiledParams p, Frames f) {
     const int A = cs.x - n * imc;                         // sum (c - imc)
 
     unsigned long long best = 0ull;
-    for (int base = (warp / GX) * 32; base < ntasks; base += kWarpsPerBlk * 32) {
-      // pruning threshold: the best score any lane of this warp has seen (positive floats order
-      // like their bit patterns)
+    // one task: NV vertically adjacent candidates at column dxi, the first one at window row dy0
+    auto task = [&](auto nv_tag, auto masked_tag, const int dxi, const int dy0, const float thr, const int nrows) {
+      constexpr int NV = decltype(nv_tag)::value;
+      // only the masked instantiation (the tail group) tests for rows that do not exist
+      const int nvalid = decltype(masked_tag)::value ? nrows : NV;
+      const int dx = dx_lo + dxi;
+      const int u = e + blk * BW + dx;                      // byte column inside a window row
+      const uint32_t shift = 8u * (uint32_t)(u & 3);
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(s_win + dy0 * PITCH) + (u >> 2);
+      constexpr int pitchw = PITCH >> 2;
+      // table entries of the candidates (issued early; consumed after the dot products)
+      int2 st[NV];
+      {
+        const int2 *tp = p.table + (size_t)pair * p.table_pair_stride +
+                         (size_t)(y0 - p.R + dy0 - p.table_y_lo) * p.W + (x0 - p.R + dx);
+#pragma unroll
+        for (int v = 0; v < NV; v++) st[v] = v < nvalid ? __ldg(tp + (size_t)v * p.W) : make_int2(0, 0);
+      }
+      uint32_t acc[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) acc[v] = 0u;
+#pragma unroll
+      for (int row = 0; row < BH + NV - 1; row++) {
+        uint32_t raw[WORDS + 1], rw[WORDS];
+#pragma unroll
+        for (int w = 0; w <= WORDS; w++) raw[w] = rowp[row * pitchw + w];
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) rw[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          const int r = row - v;               // current-block row this window row meets for candidate v
+          if (r >= 0 && r < BH) {
+#pragma unroll
+            for (int w = 0; w < WORDS; w++) acc[v] = __dp4a(cw[r][w], rw[w], acc[v]);
+          }
+        }
+      }
+      // ---- per candidate: cross term, cheap bound, and only then the full score (ssim.c:54-58)
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        if (v >= nvalid) break;
+        const int sumr = st[v].x;
+        const float sr = __int_as_float(st[v].y);
+        const int imr = sumr >> kLogN;                             // (int)mean, ssim.c:54
+        const int is = (int)acc[v] - imr * A - imc * sumr;          // sum (r - imr)(c - imc), exact
+        const float cross = __fmul_rn((float)is, inv_n);            // ssim.c:39
+        const float num = __fadd_rn(cross, kC3());
+        const float den = __fadd_rn(__fmul_rn(sr, sc), kC3());
+        if (!(__fmul_rn(num, kPruneMargin()) < __fmul_rn(thr, den))) {
+          const float mr = __fmul_rn((float)sumr, inv_n);           // ssim.c:12
+          const float s = ssim_from_stats(mr, sr, mc, sc, cross);
+          if (s > 0.0f) {
+            const uint32_t vis = (uint32_t)((dy0 + v - dy_lo) << 16) | (uint32_t)dxi;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - vis);
+            best = key > best ? key : best;
+          }
+        }
+      }
+    };
+    // pruning threshold of a pass: the best score any lane of this warp has seen so far
+    // (positive floats order like their bit patterns)
+    const int nfull = ncx * ngy;
+    for (int base = (warp / GX) * 32; base < nfull; base += kWarpsPerBlk * 32) {
       const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, (uint32_t)(best >> 32)));
       const int t = base + lane;
-      if (t < ntasks) {
+      if (t < nfull) {
         int gy = t / ncx;
         const int dxi = t - gy * ncx;
         gy += gy_first;
         if (gy >= ngy) gy -= ngy;
-        const int dx = dx_lo + dxi, dy0 = dy_lo + gy * VB;   // window-relative offsets of the first candidate
-        const int u = e + blk * BW + dx;                      // byte column inside a window row
-        const uint32_t shift = 8u * (uint32_t)(u & 3);
-        const uint32_t *rowp = reinterpret_cast<const uint32_t *>(s_win + dy0 * PITCH) + (u >> 2);
-        constexpr int pitchw = PITCH >> 2;
-        // table entries of the VB candidates (issued early; consumed after the dot products)
-        int2 st[VB];
-        {
-          const int2 *tp = p.table + (size_t)pair * p.table_pair_stride +
-                           (size_t)(y0 - p.R + dy0 - p.table_y_lo) * p.W + (x0 - p.R + dx);
-#pragma unroll
-          for (int v = 0; v < VB; v++)
-            st[v] = (dy0 + v <= dy_hi) ? __ldg(tp + (size_t)v * p.W) : make_int2(0, 0);
-        }
-        uint32_t acc[VB];
-#pragma unroll
-        for (int v = 0; v < VB; v++) acc[v] = 0u;
-#pragma unroll
-        for (int row = 0; row < BH + VB - 1; row++) {
-          uint32_t raw[WORDS + 1], rw[WORDS];
-#pragma unroll
-          for (int w = 0; w <= WORDS; w++) raw[w] = rowp[row * pitchw + w];
-#pragma unroll
-          for (int w = 0; w < WORDS; w++) rw[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
-#pragma unroll
-          for (int v = 0; v < VB; v++) {
-            const int r = row - v;             // current-block row this window row meets for candidate v
-            if (r >= 0 && r < BH) {
-#pragma unroll
-              for (int w = 0; w < WORDS; w++) acc[v] = __dp4a(cw[r][w], rw[w], acc[v]);
-            }
-          }
-        }
-        // ---- per candidate: cross term, cheap bound, and only then the full score (ssim.c:54-58)
-#pragma unroll
-        for (int v = 0; v < VB; v++) {
-          if (dy0 + v <= dy_hi) {
-            const int sumr = st[v].x;
-            const float sr = __int_as_float(st[v].y);
-            const int imr = sumr >> kLogN;                             // (int)mean, ssim.c:54
-            const int is = (int)acc[v] - imr * A - imc * sumr;          // sum (r - imr)(c - imc), exact
-            const float cross = __fmul_rn((float)is, inv_n);            // ssim.c:39
-            const float num = __fadd_rn(cross, kC3());
-            const float den = __fadd_rn(__fmul_rn(sr, sc), kC3());
-            if (!(__fmul_rn(num, kPruneMargin()) < __fmul_rn(thr, den))) {
-              const float mr = __fmul_rn((float)sumr, inv_n);           // ssim.c:12
-              const float s = ssim_from_stats(mr, sr, mc, sc, cross);
-              if (s > 0.0f) {
-                const uint32_t vis = (uint32_t)((dy0 + v - dy_lo) << 16) | (uint32_t)dxi;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | (0xffffffffu - vis);
-                best = key > best ? key : best;
-              }
-            }
-          }
-        }
+        // with a masked tail group every group of the block takes the masked instantiation: full and
+        // tail groups share passes, and two code paths in one warp would run one after the other
+        if (!tail_group) task(std::integral_constant<int, VB>{}, std::false_type{}, dxi, dy_lo + gy * VB, thr, VB);
+        else task(std::integral_constant<int, VB>{}, std::true_type{}, dxi, dy_lo + gy * VB, thr, min(VB, ncy - gy * VB));
       }
     }
+    // the ncy % VB rows below the full groups: binary decomposition into groups of 4, 2 and 1
+    auto rest = [&](auto nv_tag, const int dy0) {
+      for (int base = (warp / GX) * 32; base < ncx; base += kWarpsPerBlk * 32) {
+        const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, (uint32_t)(best >> 32)));
+        const int dxi = base + lane;
+        if (dxi < ncx) task(nv_tag, std::false_type{}, dxi, dy0, thr, decltype(nv_tag)::value);
+      }
+    };
+    int dy_rest = dy_lo + ngy_full * VB;
+    static_assert(VB == 8, "the leftover decomposition below assumes groups of 8");
+    if (nleft & 4) {
+      rest(std::integral_constant<int, 4>{}, dy_rest);
+      dy_rest += 4;
+    }
+    if (nleft & 2) {
+      rest(std::integral_constant<int, 2>{}, dy_rest);
+      dy_rest += 2;
+    }
+    if (nleft & 1) rest(std::integral_constant<int, 1>{}, dy_rest);
     best = shfl_max_u64(best);
     if (lane == 0 && best != 0ull) atomicMax(&best_s[blk], best);
   }
@@ -548,7 +583,7 @@ cudaError_t launch_ssim_tiled_pitch(const Geom &g, const Frames &f, int npairs, 
   p.nbx_full = g.W / BW;
   const int groups_per_row = (p.nbx_full + GX - 1) / GX;
   p.win_pitch = (GX * BW + 2 * g.R + 4 + 3 + 4) & ~3;  // + alignment slack on the left
-  p.win_rows = 2 * g.R + BH + VB;
+  p.win_rows = 2 * g.R + BH + VB;   // a few zero rows of slack below the last candidate
   p.out = o;
   // statistics table: rows [y_lo, y_hi] of the positions that this band can touch
   int y_lo = by_begin * g.B - g.R, y_hi = (by_begin + by_count - 1) * g.B + g.R;
