@@ -14,6 +14,8 @@
 //   * key = ssd << 8 | raster index of the candidate in the (2R+1)^2 grid, one 32-bit shared
 //     atomicMin per candidate; the unsigned minimum is the reference's first strict minimum in
 //     y-major/x-minor order (main.c:53-62) because clamped-away candidates are simply skipped.
+#include <stdlib.h>
+
 #include "me_device.cuh"
 
 namespace me {
@@ -212,6 +214,74 @@ direct_search_kernel(Geom g, Frames f, Out o) {
   }
 }
 
+// ---- R = 0: the purely memory-bound end.  The only candidate of a block is the co-located one
+// (main.c:73-76 clamp the window to the block itself), so the search is one streaming pass over
+// both frames straight from global memory (aligned: dx = 0), VABSDIFF4 + IDP.4A.  A warp owns the
+// 128 / B blocks that span 128 contiguous bytes of one block row: every load instruction of the
+// warp fetches whole 128-byte lines (LPR lanes per row, 32 / LPR rows per instruction), all
+// B / (32 / LPR) = 4 loads per frame of a lane are issued before the first is consumed, and the
+// lanes that hold the rows of one block are added with two or one shuffles.  ~60 instructions per
+// 128 input bytes of a lane: the kernel sits on the HBM roof, not on the issue rate like the
+// staged kernel above.
+template <int B, int LPR>
+__global__ void __launch_bounds__(256)
+zero_span_kernel(Geom g, Frames f, Out o, int nbx_groups) {
+  // LPR = lanes (= blocks) per row piece of a warp: LPR * B contiguous bytes per row
+  constexpr int RPI = 32 / LPR;                     // rows per load instruction: 4 or 2
+  constexpr int NIT = B / RPI;                      // load instructions per frame: 4
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int bc = lane % LPR, rq = lane / LPR;
+  const int wx = warp % nbx_groups, wy = warp / nbx_groups;     // warp -> (group of LPR blocks, block row)
+  if (wy >= g.by_count) return;
+  const int by = g.by_begin + wy;
+  const int bx = wx * LPR + bc;
+  const int x0 = bx * B, y0 = by * B;
+  const bool blk_ok = bx < g.nbx;
+  const int w = blk_ok ? min(B, g.W - x0) : 0, h = min(B, g.H - y0);
+  const size_t base = (size_t)blockIdx.y * f.pair_stride + (size_t)y0 * f.pitch + x0;
+  uint32_t c[NIT][B / 4], r[NIT][B / 4];
+#pragma unroll
+  for (int i = 0; i < NIT; i++) {
+    const int row = i * RPI + rq;
+    const size_t off = base + (size_t)row * f.pitch;
+#pragma unroll
+    for (int k = 0; k < B / 4; k++) c[i][k] = r[i][k] = 0u;
+    if (w == B && row < h) {
+      if constexpr (B == 16) {
+        const uint4 cv = *reinterpret_cast<const uint4 *>(f.cur + off), rv = *reinterpret_cast<const uint4 *>(f.ref + off);
+        c[i][0] = cv.x; c[i][1] = cv.y; c[i][2] = cv.z; c[i][3] = cv.w;
+        r[i][0] = rv.x; r[i][1] = rv.y; r[i][2] = rv.z; r[i][3] = rv.w;
+      } else {
+        const uint2 cv = *reinterpret_cast<const uint2 *>(f.cur + off), rv = *reinterpret_cast<const uint2 *>(f.ref + off);
+        c[i][0] = cv.x; c[i][1] = cv.y;
+        r[i][0] = rv.x; r[i][1] = rv.y;
+      }
+    } else if (w > 0 && row < h) {  // partial-width block at the right frame edge: columns >= w do not exist
+      for (int b = 0; b < w; b++) {
+        c[i][b >> 2] |= (uint32_t)f.cur[off + b] << (8 * (b & 3));
+        r[i][b >> 2] |= (uint32_t)f.ref[off + b] << (8 * (b & 3));
+      }
+    }
+  }
+  uint32_t ssd = 0;
+#pragma unroll
+  for (int i = 0; i < NIT; i++)
+#pragma unroll
+    for (int k = 0; k < B / 4; k++) {
+      const uint32_t d = __vabsdiffu4(c[i][k], r[i][k]);   // rows that do not exist are 0 vs 0
+      ssd = __dp4a(d, d, ssd);
+    }
+#pragma unroll
+  for (int s_ = LPR; s_ < 32; s_ <<= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, s_);
+  if (blk_ok && rq == 0) {
+    const size_t oi = (size_t)blockIdx.y * g.nbx * g.nby + (size_t)by * g.nbx + bx;
+    if (o.mvx) o.mvx[oi] = 0;      // main.c:58-59: the only candidate is the block's own position
+    if (o.mvy) o.mvy[oi] = 0;
+    if (o.ssd) o.ssd[oi] = ssd;
+    if (o.score) o.score[oi] = __fdiv_rn((float)ssd, (float)(w * h));  // main.c:27
+  }
+}
+
 }  // namespace
 
 bool direct_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
@@ -237,7 +307,28 @@ cudaError_t launch_direct(const Geom &g, const Frames &f, int npairs, const Out 
     if (oo.ssd) oo.ssd += off;
     if (oo.score) oo.score += off;
     dim3 grid((g.W + kTX - 1) / kTX, (rows_px + kTY - 1) / kTY, n);
-    if (g.R == 0) {
+    // R = 0 on a 16-byte aligned layout: the streaming kernel
+    const bool stream_ok = g.R == 0 && (f.pitch & 15) == 0 && (f.pair_stride & 15) == 0 &&
+                           ((((uintptr_t)f.cur) | ((uintptr_t)f.ref)) & 15) == 0;
+    if (stream_ok) {
+      // blocks of one warp (LPR), measured on 4K / 1080p batches: 16x16: 2 (32-byte row pieces, all 16
+      // rows in one load instruction: 4.9 TB/s; 4 or 8 blocks: 2.8-3.0 TB/s); 8x8: 8 (64-byte pieces,
+      // 4 rows per instruction: 3.6 TB/s; 4 or 16 blocks: 2.7 TB/s)
+      int bpw = g.B == 16 ? 2 : 8;
+      if (const char *e = getenv("ME_B200_R0_LPR")) bpw = atoi(e);
+      const int nbx_groups = (g.nbx + bpw - 1) / bpw;
+      const long long warps = (long long)nbx_groups * g.by_count;
+      dim3 zg((unsigned)((warps + 7) / 8), (unsigned)n);
+      if (g.B == 16) {
+        if (bpw == 8) zero_span_kernel<16, 8><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+        else if (bpw == 4) zero_span_kernel<16, 4><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+        else zero_span_kernel<16, 2><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+      } else {
+        if (bpw == 4) zero_span_kernel<8, 4><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+        else if (bpw == 8) zero_span_kernel<8, 8><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+        else zero_span_kernel<8, 16><<<zg, 256, 0, s>>>(g, ff, oo, nbx_groups);
+      }
+    } else if (g.R == 0) {
       if (g.B == 16) direct_search_kernel<16, true><<<grid, kThreads, 0, s>>>(g, ff, oo);
       else direct_search_kernel<8, true><<<grid, kThreads, 0, s>>>(g, ff, oo);
     } else {
