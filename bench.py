@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                     pass
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            while not self.stop_flag:
+            while True:   # at least one sample even when the timed region is shorter than the start-up
                 mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -107,6 +107,8 @@ class ClockSampler(threading.Thread):
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
                 self.rows.append((float(mhz), int(reasons), watts))
+                if self.stop_flag:
+                    break
                 time.sleep(0.004)
         except Exception as ex:  # pragma: no cover
             self.err = repr(ex)
@@ -309,6 +311,8 @@ def main():
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag = True
+    if rank == 0:
+        sampler.join(timeout=2.0)
     launches = est.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     dev_ms = float(sum(step_ms))                      # device time of the K steps on this rank
