@@ -33,6 +33,14 @@ def test_reference_arm_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
 
 
+@pytest.mark.parametrize("workload,kind", [("diamond_foreman_8x8_pm12", "port")])
+def test_reference_arm_of_the_widened_rows(workload, kind):
+    """Fast patterns have no reference implementation: their CPU arm is the definition's port."""
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", workload)
+    assert d["impl"] == "reference" and d["config"]["workload"] == workload and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == kind and d["gpu_launches"] == 0
+
+
 def test_reference_arm_other_ranks_are_silent():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
@@ -53,3 +61,14 @@ def test_b200_arm_line():
     e = d["e2e"]
     assert e["value"] > 500 and e["h2d_bytes_per_step"] == 2 * 4 * 1920 * 1080 and e["d2h_bytes_per_step"] > 0
     assert "clocks" in d and "reasons" in d["clocks"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload,pairs", [("ssim_1080p_16x16_pm32", "4"), ("diamond_1080p_16x16_pm32", "8")])
+def test_b200_arm_widened_rows(workload, pairs):
+    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", pairs, "--no-cpu-baseline", "--workload", workload)
+    assert BASE_KEYS <= set(d) and d["config"]["workload"] == workload
+    assert d["value"] > 100 and d["e2e"]["value"] > 100 and d["gpu_launches"] >= 2
+    assert d["config"]["cost"] in ("mse", "ssim") and d["config"]["search"] in ("full", "three_step", "diamond")
+    if d["config"]["search"] != "full":
+        assert d["candidate_evaluations_per_s"] > 1e8
