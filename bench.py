@@ -45,6 +45,10 @@ WORKLOADS = {
     "foreman_8x8_pm12": (352, 288, 8, 12, 512, "BASELINE configs[0]: Foreman YF2->YF1, reference defaults 8x8 +-12"),
     # the only configuration the reference publishes numbers for: 3840x2160, 8x8, +-12
     "4k_8x8_pm12": (3840, 2160, 8, 12, 16, "reference's own published runs: synthetic 3840x2160 luma, 8x8 blocks, full search +-12"),
+    # the memory-bound end (north_star's "memory-bound small-range cases"): the
+    # only candidate is the co-located block, one streaming pass over both frames
+    "1080p_16x16_pm0": (1920, 1080, 16, 0, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-0"),
+    "4k_16x16_pm0": (3840, 2160, 16, 0, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-0"),
     # SSIM-cost full search (src/cpu/main_ssim.c); the first one is that program's default geometry
     "ssim_4k_16x16_pm7": (3840, 2160, 16, 7, 8, "reference SSIM program defaults (main_ssim.c:41-44): synthetic 3840x2160 luma, blk 16, span 7"),
     "ssim_1080p_16x16_pm32": (1920, 1080, 16, 32, 16, "SSIM-cost full search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),
@@ -448,6 +452,28 @@ def main():
                 traffic = json.load(f)[name]["bytes_per_pair"] * pairs
         except Exception:
             pass
+        # measured copy bandwidth of this pool's B200s (driver-written), else the profiling guide's fallback
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+        except Exception:
+            pass
+        roofline = {"bound": "int_alu", "achieved": achieved / 1e12, "peak": pair_rate / 1e12,
+                    "unit": "T lane-instr/s", "frac": achieved / pair_rate if pair_rate else None,
+                    "traffic": traffic,
+                    "peak_source": "measured live: me_b200_int_peak(%s) at %.0f MHz" % (what, mhz),
+                    "frac_of_single_pipe_peak": (achieved / (pair_rate / 2) if pair_rate else None) if cost == 0 else None,
+                    "note": ("fast search: a few dependent steps per block, latency bound by design; "
+                             "the fraction only says how little arithmetic a fast search needs") if search else None,
+                    "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": hbm_peak,
+                            "algorithmic_bytes_per_step": alg_bytes}}
+        if R == 0 and not cost and not search:
+            # one candidate per block: a streaming pass, bound by HBM
+            roofline = {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / step_s / 1e9 / hbm_peak, "traffic": traffic,
+                        "peak_source": hbm_src,
+                        "int_alu": {"achieved_t_lane_instr_s": achieved / 1e12, "peak": pair_rate / 1e12}}
         line = {
             "metric": METRIC if name == "1080p_16x16_pm32" else name + "_frames_per_sec",
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -473,15 +499,7 @@ def main():
                              "h2d_bytes_per_step": nslots * (slot_pairs + 1) * n,
                              "api": "me_b200_submit_sequence: pair i = frame i+1 vs frame i, each frame uploaded once"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": pair_rate / 1e12,
-                         "unit": "T lane-instr/s", "frac": achieved / pair_rate if pair_rate else None,
-                         "traffic": traffic,
-                         "peak_source": "measured live: me_b200_int_peak(%s) at %.0f MHz" % (what, mhz),
-                         "frac_of_single_pipe_peak": (achieved / (pair_rate / 2) if pair_rate else None) if cost == 0 else None,
-                         "note": ("fast search: a few dependent steps per block, latency bound by design; "
-                                  "the fraction only says how little arithmetic a fast search needs") if search else None,
-                         "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": 6455.9,
-                                 "algorithmic_bytes_per_step": alg_bytes}},
+            "roofline": roofline,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
