@@ -119,11 +119,12 @@ def test_ssim_device_path_bands_and_batches(orc):
         check(out, p, exp[p]["mvx"], exp[p]["mvy"], exp[p]["ssd"], exp[p]["score"].view(np.uint32), f"pair {p}")
 
 
-@pytest.mark.parametrize("B,R", [(16, 7), (16, 32), (8, 12)])
-def test_ssim_full_size_1080p(orc, B, R):
-    """1080p (half-height bottom row at B = 16): the tuned path equals the pinned restatement on the
-    first, a middle and the last block rows, and equals the generic kernel everywhere."""
-    W, H = 1920, 1080
+@pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 7), (1920, 1080, 16, 32), (1920, 1080, 8, 12),
+                                     (3840, 2160, 16, 7)])   # the last one = main_ssim.c's own defaults
+def test_ssim_full_size(orc, W, H, B, R):
+    """Full-size frames (1080p: half-height bottom row at B = 16; 4K at the SSIM program's default
+    block size and span): the tuned path equals the pinned restatement on the first, a middle and
+    the last block rows, and equals the generic kernel everywhere."""
     cur, ref = me.tiled_frames(W, H)
     with me.Estimator(W, H, B, R, cost=me.ME_COST_SSIM) as est:
         out = est.search_u8(cur, ref)
