@@ -76,6 +76,13 @@ constexpr int kWinPitch = 256;  // window row pitch in shared memory = TMA box w
                                 // a compile-time pitch turns every row offset into an LDS immediate
 constexpr uint32_t kNoKey = 0xffffffffu;
 constexpr int kMaxPeerOuts = 7;  // other GPUs of one NVSwitch domain
+// FORM 2 with 8x8 blocks (64 pixels): the energy table holds E + kBias8, and a finished candidate is
+// ranked by t = (E + kBias8) - 2*dot instead of the full SSD = sum cur^2 + E - 2*dot.  sum cur^2 is
+// the same for every candidate of a block, so the order (and every tie) is unchanged, but the
+// finish is LDS + IADD3 + PRMT + VIMNMX with nothing on the FMA-heavy pipe, and no task computes
+// sum cur^2 at all; the publishing lane adds it back once per block.  2*dot <= 2*64*255^2 <
+// kBias8 = 2^23 keeps t >= 0, and t <= 64*255^2 + 2^23 < 2^24 keeps it inside the 24-bit key field.
+constexpr uint32_t kBias8 = 1u << 23;
 
 struct TiledParams {
   int W, H, B, R;
@@ -332,7 +339,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
       uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
       const bool half = I.h != BH;          // bottom block row of height BH/2
-      if (FORM >= 1) {
+      constexpr bool kBiased = FORM == 2 && BH == 8;   // see kBias8
+      if (FORM >= 1 && !kBiased) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
           uint32_t a4[4] = {0u, 0u, 0u, 0u};  // four independent IDP chains instead of one long one
@@ -435,10 +443,19 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
                 if (FORM == 1) ssd = srun[b] - 2u * a;
                 if (FORM == 2) {
                   // (A + E) - a - a: one IADD3 on the ALU pipe instead of an IMAD on the saturated FMA pipe
-                  const uint32_t ae = srun[b] + spf[b * BW];
+                  // (8x8: the table entry already holds E + kBias8 and A is added back at publish time)
+                  const uint32_t ae = kBiased ? spf[b * BW] : srun[b] + spf[b * BW];
                   asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %2; }" : "=r"(ssd) : "r"(ae), "r"(a));
                 }
-                const uint32_t key = (ssd << 8) + (uint32_t)(dy_fin + s_);
+                uint32_t key;
+                if constexpr (BH == 8) {
+                  // ssd < 2^24 and dy < 2^8: a byte permute builds ssd << 8 | dy on the ALU pipe.  Left
+                  // to itself ptxas emits IMAD(ssd, 0x100, dy) here -- on the FMA-heavy pipe the
+                  // IDP.4A stream already saturates, where 8x8 blocks finish a candidate every 16 IDP
+                  key = __byte_perm(ssd, (uint32_t)(dy_fin + s_), 0x2104);
+                } else {
+                  key = (ssd << 8) + (uint32_t)(dy_fin + s_);
+                }
                 bestk[b] = min(bestk[b], key);
               }
             }
@@ -498,7 +515,21 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         if (bx < p.nbx) {
           const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[b]);
           const uint32_t k32 = (uint32_t)(key >> 32);
-          const uint32_t ssd = k32 >> 8;
+          uint32_t ssd = k32 >> 8;
+          if constexpr (FORM == 2 && BH == 8) {
+            // un-bias: ssd = t - kBias8 + sum cur^2 of this block, from the stage's current tile (rows
+            // below a half-height block are zero-filled by the TMA load)
+            const uint32_t *ct = reinterpret_cast<const uint32_t *>(sb + cur_off) + b * (BW / 4);
+            uint32_t a2 = 0;
+#pragma unroll
+            for (int r = 0; r < BH; r++)
+#pragma unroll
+              for (int w = 0; w < BW / 4; w++) {
+                const uint32_t v = ct[r * (p.cur_pitch >> 2) + w];
+                a2 = __dp4a(v, v, a2);
+              }
+            ssd = ssd - kBias8 + a2;
+          }
           const size_t oi = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
           if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
           if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
@@ -541,7 +572,8 @@ constexpr int kEWords = (kEx + kEMax) / 4;  // aligned words per staged row
 
 __global__ void __launch_bounds__(256)
 box_energy_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_stride, int W, int H, int bw, int bh,
-                  int y_lo, int nrows, uint32_t *__restrict__ out, int out_pitch, size_t out_pair_stride) {
+                  int y_lo, int nrows, uint32_t *__restrict__ out, int out_pitch, size_t out_pair_stride,
+                  uint32_t bias) {
   __shared__ uint32_t px[kEy + kEMax - 1][kEWords];   // pixels, 4 per word
   __shared__ uint32_t ws[kEy + kEMax - 1][kEWords];   // sum of squares of each aligned word
   __shared__ uint32_t hs[kEy + kEMax - 1][kEx];       // horizontal box sums
@@ -587,7 +619,7 @@ box_energy_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_str
   const int c = threadIdx.x;  // one column per thread
   if (c < kEx && x0 + c < out_pitch) {
     uint32_t *dst = out + (size_t)blockIdx.z * out_pair_stride + (size_t)r0 * out_pitch + x0 + c;
-    uint32_t a = 0;
+    uint32_t a = bias;   // constant added to every entry (kBias8 for 8x8 blocks, else 0)
     for (int k = 0; k < bh; k++) a += hs[k][c];
     dst[0] = a;
     for (int r = 1; r < rows_out; r++) {
@@ -838,13 +870,14 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     if (nfull > 0) {
       dim3 eg((tp + kEx - 1) / kEx, (nfull + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH, y_lo, nfull, d_s, tp,
-                                           per_pair);
+                                           per_pair, BH == 8 ? kBias8 : 0u);
       plan->kernels_launched++;
     }
     if (nhalf > 0) {
       dim3 eg((tp + kEx - 1) / kEx, (nhalf + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH / 2,
-                                           g.H - BH / 2 - g.R, nhalf, d_s + (size_t)tp * nfull, tp, per_pair);
+                                           g.H - BH / 2 - g.R, nhalf, d_s + (size_t)tp * nfull, tp, per_pair,
+                                           BH == 8 ? kBias8 : 0u);
       plan->kernels_launched++;
     }
     e = cudaGetLastError();
