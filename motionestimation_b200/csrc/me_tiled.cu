@@ -152,12 +152,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 
 // ---------------------------------------------------------------- item geometry
-struct Item {
+struct __align__(16) Item {
   int pair, by, strip0, ns;  // ns = strips actually present in this item
   int y0, h;                 // top pixel row of the block row, block height (BH or BH/2)
   int dy_lo, nc;             // first valid window-relative row offset, number of vertical candidates
   int m, nparts;             // part length = m*BH + 1
   int ntasks, nchunks, tpp;  // tpp = tasks per part
+  int pad_[3];               // 16 ints: four 16-byte shared-memory loads
 };
 
 template <int BH>
@@ -201,6 +202,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   __shared__ uint32_t chunk_ctr[kMaxStages];              // next 32-task chunk of the stage's item
   __shared__ uint32_t left_ctr[kMaxStages];               // warps that are done with the stage's item
   __shared__ int item_id[kMaxStages];                     // item held by the stage, -1 = no more work
+  __shared__ Item item_s[kMaxStages];                     // its decoded geometry (five integer divisions: decoded
+                                                          // once by the re-arming warp, not by all 16 warps)
 
   const int lane = threadIdx.x & 31;
   const int cur_off = p.win_bytes;                       // byte offsets inside a stage
@@ -232,6 +235,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       chunk_ctr[stage] = 0;
       left_ctr[stage] = 0;
       item_id[stage] = it;
+      item_s[stage] = I;
     }
     __syncwarp();
     if (lane == 0) {
@@ -286,7 +290,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       dead |= 1u << stage;
       continue;
     }
-    const Item I = decode_item<BH>(p, it);
+    const Item I = item_s[stage];
 
     const int L = I.m * BH + 1;
     const int ndx = 2 * p.R + 1;
