@@ -158,7 +158,8 @@ struct __align__(16) Item {
   int dy_lo, nc;             // first valid window-relative row offset, number of vertical candidates
   int m, nparts;             // part length = m*BH + 1
   int ntasks, nchunks, tpp;  // tpp = tasks per part
-  int pad_[3];               // 16 ints: four 16-byte shared-memory loads
+  unsigned inv_ns;           // ceil(2^32 / ns): row / ns by multiply-high (rows < 2^16)
+  int pad_[2];               // 16 ints: four 16-byte shared-memory loads
 };
 
 template <int BH>
@@ -183,6 +184,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
   const int L = I.m * BH + 1;
   I.nparts = (I.nc + L - 1) / L;
   I.tpp = I.ns * (2 * p.R + 1);
+  I.inv_ns = (unsigned)((0x100000000ull + (unsigned)I.ns - 1) / (unsigned)I.ns);
   I.ntasks = I.tpp * I.nparts;
   I.nchunks = (I.ntasks + 31) >> 5;
   return I;
@@ -308,7 +310,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // task = (part * ns + strip) * ndx + dx; ndx divides by multiply-high (tasks < 2^16)
       const int row = (int)__umulhi((unsigned)task, p.inv_ndx);  // = part * ns + strip
       const int dx = task - row * ndx;        // window-relative horizontal offset, mvx = dx - R
-      const int part = row / I.ns;
+      const int part = I.ns == 1 ? row : (int)__umulhi((unsigned)row, I.inv_ns);  // (2^32 / 1 does not fit)
       const int st = row - part * I.ns;
       const int u = p.e + st * SW + dx;       // byte offset of the candidate column in a window row
       const uint32_t shift = 8u * (uint32_t)(u & 3);
