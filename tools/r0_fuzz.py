@@ -1,7 +1,16 @@
-import sys, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
-import numpy as np, motionestimation_b200 as me
-from oracle_binding import Oracle
+"""Randomised parity fuzz of the +-0 streaming kernel (zero_span_kernel) against the oracle:
+random frame sizes incl. partial right/bottom blocks, batches of 1..3 pairs.
+usage: python tools/r0_fuzz.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import motionestimation_b200 as me  # noqa: E402
+from oracle_binding import Oracle  # noqa: E402
+
 orc=Oracle(); rng=np.random.Generator(np.random.PCG64(5)); bad=0
 for i in range(120):
     B=int(rng.choice([8,16])); W=int(rng.integers(B,300)); H=int(rng.integers(B,200))
