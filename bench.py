@@ -494,7 +494,9 @@ def main():
                     "api": "me_b200_submit/me_b200_wait, pinned u8 host frames, %d slots x %d pairs, the K steps "
                            "streamed through the slot ring (upload of batch i+1 overlaps the search of batch i)"
                            % (nslots, slot_pairs),
-                    "step_synchronous": e2e_sync_fps},
+                    "step_synchronous": e2e_sync_fps,
+                    # host->device traffic the streamed run actually sustained (per GPU)
+                    "h2d_gbs_per_gpu": 2 * pairs * n * (e2e_fps / world / pairs) / 1e9},
             "e2e_sequence": {"value": seq_fps, "unit": "frames/s",
                              "h2d_bytes_per_step": nslots * (slot_pairs + 1) * n,
                              "api": "me_b200_submit_sequence: pair i = frame i+1 vs frame i, each frame uploaded once"},
