@@ -389,3 +389,31 @@ def test_int_peak_microbenchmarks_run():
     for which in (0, 1, 2):
         rate, mhz = me.int_peak(which, iters=200)
         assert rate > 1e12 and 500 < mhz < 3000
+
+
+def test_search_is_cuda_graph_capturable(orc):
+    """The device-resident call is stream-ordered end to end (stream-ordered scratch, tensor maps
+    passed by value): it can be captured into a CUDA graph once and replayed on new frame contents."""
+    torch = _torch()
+    W, H, B, R = 352, 288, 8, 12
+    cur8, ref8 = me.foreman(2), me.foreman(1)
+    cur, ref = torch.from_numpy(cur8).cuda(), torch.from_numpy(ref8).cuda()
+    with me.Estimator(W, H, B, R) as est:
+        nb = est.num_blocks
+        mvx = torch.zeros((nb,), dtype=torch.int32, device="cuda")
+        mvy, ssd = torch.zeros_like(mvx), torch.zeros_like(mvx)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            est.search_device(cur, ref, W, W * H, 1, mvx, mvy, ssd, None, s.cuda_stream)   # warm-up outside capture
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                est.search_device(cur, ref, W, W * H, 1, mvx, mvy, ssd, None, s.cuda_stream)
+            # replay on other contents in the same buffers: YF4 searched in YF1
+            cur.copy_(torch.from_numpy(me.foreman(4)).cuda())
+            mvx.zero_()
+            g.replay()
+            s.synchronize()
+    exp = orc.search(me.foreman(4), ref8, B, R)
+    assert np.array_equal(mvx.cpu().numpy(), exp["mvx"]) and np.array_equal(mvy.cpu().numpy(), exp["mvy"])
+    assert np.array_equal(ssd.cpu().numpy().view(np.uint32), exp["ssd"])
