@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ME_B200_ABI_VERSION 1
+#define ME_B200_ABI_VERSION 2 /* 2: + cost / search modes, SSIM and fast drop-ins, peer fields (all additive) */
 
 /* return codes: 0 ok, negative error.  The library never prints or exits
  * (the reference printf+exit()s, main.c:110-113,134-139; utils.c:105-108). */

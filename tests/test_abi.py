@@ -42,7 +42,7 @@ def test_exports_are_plain_c():
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     for s in declared_symbols():
         assert s in exported
-    assert me.load_library().me_b200_abi_version() == 1
+    assert me.load_library().me_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_reference():
