@@ -24,6 +24,7 @@ Printed JSON line (rank 0):
 --impl reference times the reference's own CPU implementation instead (no GPU work).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -49,6 +50,10 @@ WORKLOADS = {
     # only candidate is the co-located block, one streaming pass over both frames
     "1080p_16x16_pm0": (1920, 1080, 16, 0, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-0"),
     "4k_16x16_pm0": (3840, 2160, 16, 0, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-0"),
+    "1080p_16x16_pm1": (1920, 1080, 16, 1, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-1"),
+    "1080p_16x16_pm2": (1920, 1080, 16, 2, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-2"),
+    "1080p_16x16_pm4": (1920, 1080, 16, 4, 64, "small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-4"),
+    "4k_16x16_pm2": (3840, 2160, 16, 2, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-2"),
     # SSIM-cost full search (src/cpu/main_ssim.c); the first one is that program's default geometry
     "ssim_4k_16x16_pm7": (3840, 2160, 16, 7, 8, "reference SSIM program defaults (main_ssim.c:41-44): synthetic 3840x2160 luma, blk 16, span 7"),
     "ssim_1080p_16x16_pm32": (1920, 1080, 16, 32, 16, "SSIM-cost full search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),
@@ -64,6 +69,27 @@ MODES = {"ssim_4k_16x16_pm7": (1, 0), "ssim_1080p_16x16_pm32": (1, 0), "tss_1080
 # CPU Beauty 4K 8x8 +-12 = 2350 ms (results/cpu/beauty/2990wx_threadripper_64_cores.txt:12)
 PUBLISHED_FPS = {"4k_8x8_pm12": 1000.0 / 2350.0}
 METRIC = "1080p_frames_per_sec_full_search_pm32"
+
+
+def l2_policy(name, pairs):
+    """Inputs of one step larger than L2 (126 MB), or an explicit flush between steps."""
+    W, H = WORKLOADS[name][0], WORKLOADS[name][1]
+    in_bytes = 2 * pairs * H * ((W + 15) & ~15)
+    return "inputs larger than L2" if in_bytes >= 160 * 1024 * 1024 else "L2 flushed between steps (192 MB write)"
+
+
+def workload_config(name, pairs, world):
+    """The `config` object of the JSON line -- built by BOTH arms from the workload alone, so the
+    driver's same-config check compares equal dicts."""
+    from motionestimation_b200.frames import pixel_compares
+    W, H, B, R, _, desc = WORKLOADS[name]
+    cost, search = MODES.get(name, (0, 0))
+    nb = (-(-W // B)) * (-(-H // B))
+    return {"workload": name, "desc": desc, "width": W, "height": H, "blk_dim": B, "extra_span": R,
+            "pairs_per_gpu_per_step": pairs, "blocks_per_pair": nb,
+            "pixel_compares_per_pair": int(pixel_compares(W, H, B, R)),
+            "parallelism": f"frame-pair sharding x{world}", "l2": l2_policy(name, pairs),
+            "cost": ["mse", "ssim"][cost], "search": ["full", "three_step", "diamond"][search]}
 
 
 def make_batch(name, pairs, rank):
@@ -208,13 +234,15 @@ def run_reference_arm(args):
         return
     name = args.workload
     W, H, B, R, pairs, desc = WORKLOADS[name]
+    if args.pairs > 0:
+        pairs = args.pairs
     fps, blocks_s, info = cpu_reference_rate(name, budget_s=150.0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC if name == "1080p_16x16_pm32" else name + "_frames_per_sec",
         "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": name, "desc": desc, "width": W, "height": H, "blk_dim": B, "extra_span": R},
+        "config": workload_config(name, pairs, args.gpus),
         "blocks_per_s": blocks_s,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
@@ -222,6 +250,104 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_check(name, cur_np, ref_np, B, R, mode, dev_out):
+    """Every block (MV, integer SSD / found flag, float score bits) of one pair of the timed batch --
+    the shifted-noise pair when the batch has one -- against the oracle on all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import Oracle
+    orc = Oracle()
+    p = 2 if cur_np.shape[0] > 2 else 0
+    t0 = time.perf_counter()
+    if mode[1]:
+        exp, _ = orc.search_fast(cur_np[p], ref_np[p], B, R, mode[1], nthreads=os.cpu_count())
+    elif mode[0] == 1:
+        exp = orc.search_ssim(cur_np[p], ref_np[p], B, R, nthreads=os.cpu_count())
+    else:
+        exp = orc.search(cur_np[p], ref_np[p], B, R, nthreads=os.cpu_count())
+    secs = time.perf_counter() - t0
+    got = {k: v[p].cpu().numpy() for k, v in dev_out.items()}
+    ok = (np.array_equal(got["mvx"], exp["mvx"]) and np.array_equal(got["mvy"], exp["mvy"]) and
+          np.array_equal(got["ssd"].view(np.uint32), exp["ssd"]) and
+          np.array_equal(got["score"].view(np.uint32), exp["score"].view(np.uint32)))
+    if not ok:
+        raise SystemExit("bench.py: the timed batch does NOT match the oracle (pair %d of %s)" % (p, name))
+    return {"checked": True, "pair": p, "blocks": int(exp.shape[0]),
+            "fields": ["mvx", "mvy", "ssd", "score bits"], "oracle_seconds": secs,
+            "checker": "oracle/me_oracle*.c (CPU restatement of main.c:18-82, pinned against the unmodified "
+                       "reference), all host cores, outside the timed region"}
+
+
+def band_split_leg(me, torch, dist, local, rank, world):
+    """ONE 4K 16x16 pair split by cost-balanced block-row bands over the ranks.  Two ways to complete
+    the field: one NCCL all_gather of the packed arrays, or none -- the search kernel stores every
+    block into all ranks' peer-mapped copies (NVLink) and a device-side flag barrier follows.
+    Both are checked on every rank against the unsharded search of that rank."""
+    from motionestimation_b200 import sharding
+    W, H, B = 3840, 2160, 16
+    out = {"workload": "one 3840x2160 pair, 16x16 blocks, split by block-row bands over %d GPUs" % world,
+           "unit": "ms", "timing": "CUDA events, median of 7, max over ranks"}
+    pairs = [me.tiled_frames(W, H), me.shifted_noise_pair(W, H, seed=7)]
+    d = [(torch.from_numpy(c).cuda(), torch.from_numpy(r).cuda()) for c, r in pairs]
+
+    def timed(fn):
+        ts = []
+        for i in range(7):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([sorted(ts)[len(ts) // 2]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), res
+
+    def same(res, full):
+        return all(bool(torch.equal(res[k].view(torch.int32), full[k].view(torch.int32))) for k in ("mvx", "mvy", "ssd", "score"))
+
+    for R in (32, 64):
+        with me.Estimator(W, H, B, R, device=local) as est:
+            nb = est.num_blocks
+            full = []
+            for c, r in d:
+                o = {k: torch.zeros((1, nb), dtype=torch.int32, device="cuda") for k in ("mvx", "mvy", "ssd")}
+                o["score"] = torch.zeros((1, nb), dtype=torch.float32, device="cuda")
+                est.search_device(c, r, W, W * H, 1, o["mvx"], o["mvy"], o["ssd"], o["score"])
+                full.append(o)
+            torch.cuda.synchronize()
+            t1, _ = timed(lambda i: est.search_device(d[0][0], d[0][1], W, W * H, 1, full[0]["mvx"], full[0]["mvy"],
+                                                      full[0]["ssd"], full[0]["score"]))
+            # the inputs alternate between two different pairs, so a stale or half-written field shows
+            for i in range(3):
+                sharding.search_banded(est, d[i & 1][0], d[i & 1][1], W, W * H, 1)
+            ok_n = True
+            tn, _ = timed(lambda i: sharding.search_banded(est, d[i & 1][0], d[i & 1][1], W, W * H, 1))
+            for i in range(4):
+                ok_n &= same(sharding.search_banded(est, d[i & 1][0], d[i & 1][1], W, W * H, 1), full[i & 1])
+            field = sharding.PeerField(est, 1)
+            for i in range(4):
+                sharding.search_banded_peer(est, field, d[i & 1][0], d[i & 1][1], W, W * H, 1, check=False)
+            field.check()
+            tp, _ = timed(lambda i: sharding.search_banded_peer(est, field, d[i & 1][0], d[i & 1][1], W, W * H, 1,
+                                                                check=False))
+            ok_p = True
+            for i in range(6):   # back to back, no host synchronisation in between: exercises the double buffering
+                res = sharding.search_banded_peer(est, field, d[i & 1][0], d[i & 1][1], W, W * H, 1, check=False)
+                ok_p &= same(res, full[i & 1])
+            field.check()
+            torch.cuda.synchronize()
+            field.close()
+            flag = torch.tensor([int(ok_n), int(ok_p)], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            out["pm%d" % R] = {"unsharded_ms": t1, "nccl_all_gather_ms": tn, "peer_stores_ms": tp,
+                               "identical_on_all_ranks_and_equal_to_unsharded": bool(flag[0].item() and flag[1].item())}
+            if not (flag[0].item() and flag[1].item()):
+                raise SystemExit("bench.py: band-sharded field differs from the unsharded search")
+    return out
 
 
 def main():
@@ -233,6 +359,10 @@ def main():
     ap.add_argument("--workload", default="1080p_16x16_pm32", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-band-split", action="store_true")
+    ap.add_argument("--sustained-s", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--dropin-calls", type=int, default=50, help="me_b200_search calls of the e2e_dropin leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -250,6 +380,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the search has no CPU fallback")
     torch.cuda.set_device(local)
+    os.environ["ME_B200_DEVICE"] = str(local)     # device of the implicit context of me_b200_search
+    # one slice of the host cores per rank (the feeding threads of eight ranks otherwise migrate
+    # over the whole socket); BENCH_AFFINITY=0 switches it off
+    all_cpus = sorted(os.sched_getaffinity(0))
+    affinity = None
+    if world > 1 and os.environ.get("BENCH_AFFINITY", "1") != "0" and len(all_cpus) >= 2 * world:
+        per = len(all_cpus) // world
+        affinity = all_cpus[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, affinity)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -331,11 +470,30 @@ def main():
     # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ---
     lib = me.load_library()
     n = W * H
-    h_cur = torch.from_numpy(cur_np.reshape(pairs, n)).pin_memory()
-    h_ref = torch.from_numpy(ref_np.reshape(pairs, n)).pin_memory()
-    h_mvx = torch.zeros((pairs, nb), dtype=torch.int32).pin_memory()
-    h_mvy = torch.zeros_like(h_mvx).pin_memory()
-    h_ssd = torch.zeros_like(h_mvx).pin_memory()
+    host_allocs = []
+
+    def pinned(shape, dtype, upload_only=False):
+        """numpy view of memory from me_b200_host_alloc_ex (cudaHostAlloc, allocated by this rank's own
+        thread after its affinity was set -> first touched on the rank's cores).  BENCH_WC=1: the
+        upload-only frame buffers are write-combined."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        wc = upload_only and os.environ.get("BENCH_WC", "0") == "1"
+        ptr = lib.me_b200_host_alloc_ex(nbytes, me.ME_HOST_WRITE_COMBINED if wc else 0)
+        if not ptr:
+            raise SystemExit("bench.py: me_b200_host_alloc_ex failed")
+        host_allocs.append(ptr)
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr)).view(dtype).reshape(shape)
+
+    h_cur = pinned((pairs, n), np.uint8, True)
+    h_ref = pinned((pairs, n), np.uint8, True)
+    h_cur[:] = cur_np.reshape(pairs, n)
+    h_ref[:] = ref_np.reshape(pairs, n)
+    h_mvx = pinned((pairs, nb), np.int32)
+    h_mvy = pinned((pairs, nb), np.int32)
+    h_ssd = pinned((pairs, nb), np.int32)
+    h_mvx[:] = 0
+    fsz, osz = n, nb * 4    # bytes per pair of a frame array / an output array
+    p_cur, p_ref, p_mvx, p_mvy, p_ssd = (a.ctypes.data for a in (h_cur, h_ref, h_mvx, h_mvy, h_ssd))
     nslots = min(me.lib.ME_B200_MAX_SLOTS, pairs // slot_pairs)
 
     def e2e_step():
@@ -346,8 +504,8 @@ def main():
             if inflight[s]:
                 est.wait(s)
             npp = min(slot_pairs, pairs - done)
-            est.submit_ptr(s, h_cur[done].data_ptr(), h_ref[done].data_ptr(), npp, h_mvx[done].data_ptr(),
-                           h_mvy[done].data_ptr(), h_ssd[done].data_ptr(), 0)
+            est.submit_ptr(s, p_cur + done * fsz, p_ref + done * fsz, npp, p_mvx + done * osz,
+                           p_mvy + done * osz, p_ssd + done * osz, 0)
             inflight[s] = True
             done += npp
             k += 1
@@ -368,8 +526,8 @@ def main():
                 if inflight[s]:
                     est.wait(s)
                 npp = min(slot_pairs, pairs - done)
-                est.submit_ptr(s, h_cur[done].data_ptr(), h_ref[done].data_ptr(), npp, h_mvx[done].data_ptr(),
-                               h_mvy[done].data_ptr(), h_ssd[done].data_ptr(), 0)
+                est.submit_ptr(s, p_cur + done * fsz, p_ref + done * fsz, npp, p_mvx + done * osz,
+                               p_mvy + done * osz, p_ssd + done * osz, 0)
                 inflight[s] = True
                 done += npp
                 k += 1
@@ -395,18 +553,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_fps = world * pairs * args.steps / float(t[0].item())
     e2e_sync_fps = world * pairs * args.steps / float(t[1].item())
-    assert np.array_equal(h_mvx[0].numpy(), mvx0), "e2e and device-resident paths disagree"
+    assert np.array_equal(h_mvx[0], mvx0), "e2e and device-resident paths disagree"
 
     # ---- same, for a video sequence: consecutive pairs share frames, each frame crosses PCIe once
     seq_fps = None
     if slot_pairs >= 1:
         seq = np.concatenate([ref_np[:1], cur_np[:1]] * ((slot_pairs + 2) // 2))[:slot_pairs + 1]
-        h_seq = torch.from_numpy(np.ascontiguousarray(seq).reshape(slot_pairs + 1, n)).pin_memory()
+        h_seq = pinned((slot_pairs + 1, n), np.uint8, True)
+        h_seq[:] = np.ascontiguousarray(seq).reshape(slot_pairs + 1, n)
 
         def seq_step():
             for s_ in range(nslots):
-                est.submit_sequence_ptr(s_, h_seq.data_ptr(), slot_pairs + 1, h_mvx[s_ * slot_pairs].data_ptr(),
-                                        h_mvy[s_ * slot_pairs].data_ptr(), h_ssd[s_ * slot_pairs].data_ptr(), 0)
+                est.submit_sequence_ptr(s_, h_seq.ctypes.data, slot_pairs + 1, p_mvx + s_ * slot_pairs * osz,
+                                        p_mvy + s_ * slot_pairs * osz, p_ssd + s_ * slot_pairs * osz, 0)
             for s_ in range(nslots):
                 est.wait(s_)
 
@@ -421,6 +580,75 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         seq_fps = world * nslots * slot_pairs * args.steps / float(t.item())
+
+    # ---- sustained leg: back-to-back steps for >= 3 s (no flush, no events in between) with the
+    # clock sampler running -- shows whether the clocks of the short timed region hold
+    sustained = None
+    if args.sustained_s > 0:
+        per_step_s = max(dev_ms / args.steps * 1e-3, 1e-5)
+        nsus = int(max(args.steps, min(200000, args.sustained_s / per_step_s + 1)))
+        sus_sampler = ClockSampler(local)
+        sync_all()
+        if rank == 0:
+            sus_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for i in range(nsus):
+            step()
+        s1.record(stream)
+        sync_all()
+        sus_sampler.stop_flag = True
+        if rank == 0:
+            sus_sampler.join(timeout=2.0)
+        t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus_ms = float(t.item())
+        if rank == 0:
+            sustained = {"value": world * pairs * nsus / (sus_ms * 1e-3), "unit": "frames/s", "steps": nsus,
+                         "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / nsus,
+                         "l2": "no flush between steps (inputs %s L2)" % ("exceed" if flush is None else "fit"),
+                         "clocks": sus_sampler.summary()}
+
+    # ---- the literal reference seam: me_b200_search(predictionFrame*, const int*, int) on `int`
+    # frames (main.c:132-158), one blocking call per frame pair
+    dropin = None
+    if cost == 0 and search == 0 and args.dropin_calls > 0:
+        ci = np.ascontiguousarray(cur_np[2 % pairs].astype(np.int32).ravel())
+        ri = np.ascontiguousarray(ref_np[2 % pairs].astype(np.int32).ravel())
+        pf = me.create_prediction_frame(ci, W, H, B)
+        for _ in range(3):
+            me.search_prediction_frame(pf, ri, R)
+        ncalls = args.dropin_calls
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(ncalls):
+            me.search_prediction_frame(pf, ri, R)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mv = np.array([(pf.blks[i].motion_vectorX, pf.blks[i].motion_vectorY) for i in range(0, nb, max(1, nb // 257))])
+        ref_mv = np.stack([d_mvx[2 % pairs].cpu().numpy(), d_mvy[2 % pairs].cpu().numpy()], 1)[::max(1, nb // 257)]
+        assert np.array_equal(mv, ref_mv), "drop-in and device-resident paths disagree"
+        dropin = {"value": world * ncalls / float(t.item()), "unit": "frames/s", "ms_per_call": float(t.item()) / ncalls * 1e3,
+                  "calls": ncalls, "h2d_bytes_per_call": 2 * n, "host_int_bytes_per_call": 8 * n,
+                  "api": "me_b200_search(predictionFrame*, const int*, int): blocking, int frames narrowed to u8 by "
+                         "the library's worker threads chunk by chunk while the chunks upload, search, MVs "
+                         "written into the reference's block structs"}
+
+    # ---- one very large frame split by block-row bands over the ranks: NCCL gather vs
+    # peer-mapped fields; every rank checks its complete field against the unsharded search
+    band_split = None
+    if world > 1 and not args.no_band_split:
+        band_split = band_split_leg(me, torch, dist, local, rank, world)
+
+    # ---- parity of the timed batch: every block of one pair against the oracle (outside the timed
+    # region; the oracle is only the checker)
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        parity = parity_check(name, cur_np, ref_np, B, R, (cost, search),
+                              {"mvx": d_mvx, "mvy": d_mvy, "ssd": d_ssd, "score": d_score})
 
     if rank == 0:
         # ---- roofline of the search kernel (integer pipes) -----------------
@@ -468,8 +696,9 @@ def main():
                              "the fraction only says how little arithmetic a fast search needs") if search else None,
                     "hbm": {"achieved_gbs": alg_bytes / step_s / 1e9, "peak_gbs": hbm_peak,
                             "algorithmic_bytes_per_step": alg_bytes}}
-        if R == 0 and not cost and not search:
-            # one candidate per block: a streaming pass, bound by HBM
+        if R <= 2 and not cost and not search:
+            # a handful of candidates per block (+-0..+-2 are the bandwidth-bound
+            # ranges with u8 frames): a streaming pass, bound by HBM
             roofline = {"bound": "hbm", "achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / step_s / 1e9 / hbm_peak, "traffic": traffic,
                         "peak_source": hbm_src,
@@ -480,13 +709,11 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (fps / PUBLISHED_FPS[name]) if name in PUBLISHED_FPS else None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": name, "desc": desc, "width": W, "height": H, "blk_dim": B, "extra_span": R,
-                       "pairs_per_gpu_per_step": pairs, "blocks_per_pair": nb,
-                       "pixel_compares_per_pair": pc_pair, "parallelism": f"frame-pair sharding x{world}",
-                       "l2": "inputs larger than L2" if flush is None else "L2 flushed between steps (192 MB write)",
-                       "kernel": ("warp-per-block fast search" if search else "ssim tiled + statistics pre-pass" if cost
-                                  else {1: "generic", 2: "tiled", 3: "direct"}[est.kernel_in_use]),
-                       "cost": ["mse", "ssim"][cost], "search": ["full", "three_step", "diamond"][search]},
+            "config": workload_config(name, pairs, world),
+            "kernel": ("warp-per-block fast search" if search else "ssim tiled + statistics pre-pass" if cost
+                       else {1: "generic", 2: "tiled", 3: "direct"}[est.kernel_in_use]),
+            "fallback_launches": est.fallback_launches,
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
             "blocks_per_s": fps * nb, "pixel_compares_per_s": pc_step / step_s,
             "candidate_evaluations_per_s": (fast_evals / step_s) if fast_evals is not None else None,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 2 * pairs * n,
@@ -500,17 +727,29 @@ def main():
             "e2e_sequence": {"value": seq_fps, "unit": "frames/s",
                              "h2d_bytes_per_step": nslots * (slot_pairs + 1) * n,
                              "api": "me_b200_submit_sequence: pair i = frame i+1 vs frame i, each frame uploaded once"},
+            "e2e_dropin": dropin,
+            "sustained": sustained,
+            "band_split": band_split,
+            "host": {"cpus": len(all_cpus), "affinity_of_rank0": affinity,
+                     "pinned": "me_b200_host_alloc_ex" + (" (write-combined frames)" if os.environ.get("BENCH_WC") == "1" else "")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
+        if est.fallback_launches:
+            raise SystemExit("bench.py: %d launches fell back to the generic kernel: %s"
+                             % (est.fallback_launches, lib.me_b200_last_error(est._h).decode()))
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline uses every host core
             cfps, cblocks, info = cpu_reference_rate(name, budget_s=30.0, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": info["cores"],
                                     "kind": info["kind"], "sample": info["sample"], "blocks_per_s": cblocks}
         print(json.dumps(line), flush=True)
     est.close()
+    lib.me_b200_release_cached()
+    for ptr in host_allocs:
+        lib.me_b200_host_free(ptr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -30,7 +30,9 @@
 extern "C" {
 #endif
 
-#define ME_B200_ABI_VERSION 2 /* 2: + cost / search modes, SSIM and fast drop-ins, peer fields (all additive) */
+#define ME_B200_ABI_VERSION 3 /* 2: + cost / search modes, SSIM and fast drop-ins, peer fields;
+                               * 3: + me_b200_last_kernel / _fallback_launches, batched post stage,
+                               *    me_b200_host_alloc_ex (all additive) */
 
 /* return codes: 0 ok, negative error.  The library never prints or exits
  * (the reference printf+exit()s, main.c:110-113,134-139; utils.c:105-108). */
@@ -48,7 +50,10 @@ extern "C" {
 #define ME_KERNEL_AUTO    0
 #define ME_KERNEL_GENERIC 1
 #define ME_KERNEL_TILED   2
-#define ME_KERNEL_DIRECT  3 /* small spans (R <= 4): one thread per (block, candidate) */
+#define ME_KERNEL_DIRECT  3 /* small spans (R <= 4): register-streaming kernels, the memory-bound end */
+/* reported by me_b200_last_kernel only (not selectable: they follow the context's cost / search mode) */
+#define ME_KERNEL_SSIM    4
+#define ME_KERNEL_FAST    5
 
 /* matching cost (me_b200_set_cost).  MSE: src/cpu/main.c:18-36.  SSIM: src/common/ssim.c:44-60,
  * maximised, as src/cpu/main_ssim.c runs it. */
@@ -88,7 +93,16 @@ void me_b200_destroy(me_b200_ctx *ctx);
 int      me_b200_num_blocks(const me_b200_ctx *ctx);   /* prediction_frame.c:9-12 */
 int      me_b200_blocks_x(const me_b200_ctx *ctx);
 int      me_b200_blocks_y(const me_b200_ctx *ctx);
-int      me_b200_kernel_in_use(const me_b200_ctx *ctx); /* ME_KERNEL_GENERIC, _TILED or _DIRECT */
+/* the full-search MSE kernel this context runs: of the most recent launch once there has been one
+ * (so a launch the tuned kernel could not take reports ME_KERNEL_GENERIC), before that the choice
+ * made at create time for the context's own buffers.  ME_KERNEL_GENERIC, _TILED or _DIRECT. */
+int      me_b200_kernel_in_use(const me_b200_ctx *ctx);
+/* kernel family of the most recent search launch of any mode (ME_KERNEL_*, 0 = none yet) */
+int      me_b200_last_kernel(const me_b200_ctx *ctx);
+/* ME_KERNEL_AUTO searches that the tuned kernel could not serve and the generic kernel ran instead
+ * (same results, ~10x slower); the reason of the last one is in me_b200_last_error(ctx).  0 in
+ * every supported configuration -- tests and bench.py assert it. */
+uint64_t me_b200_fallback_launches(const me_b200_ctx *ctx);
 /* exact work counts of one frame pair */
 uint64_t me_b200_pixel_compares(const me_b200_ctx *ctx);
 uint64_t me_b200_candidates(const me_b200_ctx *ctx);
@@ -161,6 +175,10 @@ int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, i
 int me_b200_search_sequence_u8(me_b200_ctx *ctx, const uint8_t *frames, int nframes,
                                int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
 void *me_b200_host_alloc(size_t bytes); /* pinned; NULL on failure */
+/* flags: ME_HOST_WRITE_COMBINED = upload-only buffers (fast for the CPU to fill sequentially and for
+ * the GPU to fetch, very slow for the CPU to read back) */
+#define ME_HOST_WRITE_COMBINED 1
+void *me_b200_host_alloc_ex(size_t bytes, int flags);
 void  me_b200_host_free(void *p);
 
 /* ---- device-resident path -----------------------------------------------------

@@ -18,6 +18,12 @@
  *     motion vector (utils.c:105-108); the drop-in CLI turns that into the
  *     reference's message + exit.
  * Implemented in plain C in motionestimation_b200/host/.
+ *
+ * Inside the reference tree: when the reference's own
+ * ../common/block.h, prediction_frame.h and utils.h have been included first (their
+ * include guards BLOCK_H / PREDICTION_FRAME_H / UTILS_H are visible), or when
+ * ME_B200_REFERENCE_TYPES is defined, this header declares nothing twice: the two
+ * structs and the src/common functions are the reference's own.
  */
 #ifndef ME_COMMON_H
 #define ME_COMMON_H
@@ -26,6 +32,11 @@
 extern "C" {
 #endif
 
+#if defined(BLOCK_H) && defined(PREDICTION_FRAME_H) && !defined(ME_B200_REFERENCE_TYPES)
+#define ME_B200_REFERENCE_TYPES 1
+#endif
+
+#ifndef ME_B200_REFERENCE_TYPES
 typedef struct block {
   int idx_x;
   int idx_y;
@@ -58,6 +69,7 @@ int yuvWriteFrame(const char *file_name, const int *const data_buffer, int numEl
 void frameDiff(int *diffFrame, const int *frameA, const int *frameB, int numElems);
 int motionCompensatedFrame(int *motionCompFrame, predictionFrame pf, const int *ref_frame);
 double imagePSNR(const int *frame1, const int *frame2, int x, int y);
+#endif /* ME_B200_REFERENCE_TYPES */
 
 /* u8 ingest without the int detour: reads numElems
  * bytes of the first luma plane straight into a byte buffer. 1 ok / 0 fail. */

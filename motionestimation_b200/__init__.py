@@ -14,6 +14,7 @@ souravBhat/MotionEstimation.
 from .lib import (  # noqa: F401
     ME_OK, ME_ERR_INVALID_ARG, ME_ERR_UNSUPPORTED, ME_ERR_CUDA, ME_ERR_NO_DEVICE,
     ME_ERR_NOMEM, ME_ERR_STATE, ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT,
+    ME_KERNEL_SSIM, ME_KERNEL_FAST, ME_HOST_WRITE_COMBINED,
     ME_COST_MSE, ME_COST_SSIM, ME_SEARCH_FULL, ME_SEARCH_THREE_STEP, ME_SEARCH_DIAMOND,
     MeError, Block, PredictionFrame, Field, load_library, library_path, device_count,
     Estimator, create_prediction_frame, search_prediction_frame, int_peak, PEAK_NAMES,

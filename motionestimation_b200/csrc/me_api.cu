@@ -6,8 +6,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "me_b200.h"
 #include "me_device.cuh"
@@ -32,6 +36,8 @@ struct me_b200_ctx {
   me_slot slots[ME_B200_MAX_SLOTS];
   me::TiledPlan *plan = nullptr;
   uint64_t launches = 0;
+  uint64_t fallback_launches = 0;  // AUTO searches the tuned kernel could not serve (generic kernel ran)
+  int last_kernel = 0;             // kernel of the most recent search launch (0: none yet)
   int cost = ME_COST_MSE;          // me_b200_set_cost
   int search = ME_SEARCH_FULL;     // me_b200_set_search
   unsigned long long *d_evals = nullptr;  // fast search: candidate evaluations so far
@@ -47,6 +53,39 @@ struct me_b200_ctx {
 namespace {
 
 char g_err[256] = {0};
+
+// one library-owned stream-ordered memory pool per device (see me_device.cuh)
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {nullptr};
+}  // namespace
+
+cudaError_t me::scratch_pool(cudaMemPool_t *pool) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    e = cudaMemPoolCreate(&g_pools[dev], &props);
+    if (e != cudaSuccess) {
+      g_pools[dev] = nullptr;
+      return e;
+    }
+    unsigned long long keep = ~0ull;   // keep the scratch between launches
+    cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    (void)cudaGetLastError();
+  }
+  *pool = g_pools[dev];
+  return cudaSuccess;
+}
+
+namespace {
 
 int fail_cuda(me_b200_ctx *ctx, cudaError_t e, const char *what) {
   char *dst = ctx ? ctx->err : g_err;
@@ -91,6 +130,7 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
     }
     if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_fast");
     ctx->launches += (uint64_t)((npairs + 65534) / 65535);
+    ctx->last_kernel = ME_KERNEL_FAST;
     return ME_OK;
   }
   if (ctx->cost == ME_COST_SSIM) {
@@ -98,6 +138,7 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
     cudaError_t e = me::launch_ssim(g, f, npairs, o, ctx->kernel_req != ME_KERNEL_GENERIC, s, &n);
     ctx->launches += n;
     if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_ssim");
+    ctx->last_kernel = ME_KERNEL_SSIM;
     return ME_OK;
   }
   // small spans: one thread per (block, candidate)
@@ -110,6 +151,7 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
     cudaError_t e = me::launch_direct(g, f, npairs, o, s);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_direct");
     ctx->launches += (uint64_t)((npairs + 65534) / 65535);
+    ctx->last_kernel = ME_KERNEL_DIRECT;
     return ME_OK;
   }
   bool tiled = ctx->kernel_req != ME_KERNEL_GENERIC && ctx->plan &&
@@ -121,15 +163,26 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
   if (tiled) {
     const char *txt = nullptr;
     cudaError_t e = me::launch_tiled(ctx->plan, g, f, npairs, o, s, &txt);
-    if (e == cudaErrorInvalidConfiguration && ctx->kernel_req != ME_KERNEL_TILED) {
-      // the geometry does not fit the tuned kernel's shared-memory ring: same results, generic kernel
+    if (e != cudaSuccess && ctx->kernel_req != ME_KERNEL_TILED && !me::tiled_plan_outputs_enqueued(ctx->plan)) {
+      // AUTO: the tuned kernel could not take this launch (window does not fit its shared-memory
+      // ring, tensor-map encode rejected the layout, scratch allocation failed ...) and nothing that
+      // writes the outputs has been enqueued: the generic kernel serves it with identical results.
+      // Never silent: counted in me_b200_fallback_launches, reason kept in me_b200_last_error,
+      // and me_b200_kernel_in_use reports ME_KERNEL_GENERIC from now on.
       (void)cudaGetLastError();
+      snprintf(ctx->err, 256, "tuned kernel not used (%s: %s); generic kernel ran", txt ? txt : "launch_tiled",
+               cudaGetErrorString(e));
+      ctx->fallback_launches++;
       tiled = false;
     } else if (e != cudaSuccess) {
       return fail_cuda(ctx, e, txt ? txt : "launch_tiled");
     }
   }
-  if (tiled) return ME_OK;  // counted by the plan (search kernel + pre-pass kernels)
+  if (tiled) {
+    ctx->last_kernel = ME_KERNEL_TILED;
+    return ME_OK;  // counted by the plan (search kernel + pre-pass kernels)
+  }
+  ctx->last_kernel = ME_KERNEL_GENERIC;
   {
     // generic kernel; grid.y carries the pair index
     int done = 0;
@@ -155,6 +208,30 @@ int run_search(me_b200_ctx *ctx, const me::Frames &f, int npairs, int by_begin, 
 
 int use_device(me_b200_ctx *ctx) {
   ME_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ME_OK;
+}
+
+// Second half of a submit, after the uploads have been queued on the slot's stream: search + the
+// downloads of the requested fields.  On a failure the stream is drained before returning, so the
+// caller's host buffers are no longer read or written once the error is reported.
+int finish_submit(me_b200_ctx *ctx, me_slot &s, const me::Frames &f, int npairs, int32_t *mvx, int32_t *mvy,
+                  uint32_t *ssd, float *score) {
+  me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
+  int rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
+  const size_t ob = (size_t)ctx->nb * (size_t)npairs * 4;
+  cudaError_t e = cudaSuccess;
+  if (rc == ME_OK && mvx) e = cudaMemcpyAsync(mvx, s.d_mvx, ob, cudaMemcpyDeviceToHost, s.stream);
+  if (rc == ME_OK && e == cudaSuccess && mvy) e = cudaMemcpyAsync(mvy, s.d_mvy, ob, cudaMemcpyDeviceToHost, s.stream);
+  if (rc == ME_OK && e == cudaSuccess && ssd) e = cudaMemcpyAsync(ssd, s.d_ssd, ob, cudaMemcpyDeviceToHost, s.stream);
+  if (rc == ME_OK && e == cudaSuccess && score)
+    e = cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream);
+  if (rc == ME_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "cudaMemcpyAsync(device to host)");
+  if (rc != ME_OK) {
+    cudaStreamSynchronize(s.stream);
+    (void)cudaGetLastError();
+    return rc;
+  }
+  s.busy = true;
   return ME_OK;
 }
 
@@ -319,7 +396,16 @@ void me_b200_destroy(me_b200_ctx *ctx) {
 int me_b200_num_blocks(const me_b200_ctx *ctx) { return ctx ? ctx->nb : 0; }
 int me_b200_blocks_x(const me_b200_ctx *ctx) { return ctx ? ctx->g.nbx : 0; }
 int me_b200_blocks_y(const me_b200_ctx *ctx) { return ctx ? ctx->g.nby : 0; }
-int me_b200_kernel_in_use(const me_b200_ctx *ctx) { return ctx ? ctx->kernel : 0; }
+int me_b200_kernel_in_use(const me_b200_ctx *ctx) {
+  if (!ctx) return 0;
+  // the kernel of the most recent full-search MSE launch; before the first launch, the choice made
+  // for the context's own buffers at create time
+  const int k = ctx->last_kernel;
+  if (k == ME_KERNEL_GENERIC || k == ME_KERNEL_TILED || k == ME_KERNEL_DIRECT) return k;
+  return ctx->kernel;
+}
+int me_b200_last_kernel(const me_b200_ctx *ctx) { return ctx ? ctx->last_kernel : 0; }
+uint64_t me_b200_fallback_launches(const me_b200_ctx *ctx) { return ctx ? ctx->fallback_launches : 0; }
 uint64_t me_b200_pixel_compares(const me_b200_ctx *ctx) {
   if (!ctx) return 0;
   return axis_sum(ctx->g.W, ctx->g.B, ctx->g.R, true) * axis_sum(ctx->g.H, ctx->g.B, ctx->g.R, true);
@@ -376,6 +462,15 @@ void *me_b200_host_alloc(size_t bytes) {
   }
   return p;
 }
+void *me_b200_host_alloc_ex(size_t bytes, int flags) {
+  void *p = nullptr;
+  const unsigned f = (flags & ME_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, f) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
 void me_b200_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
@@ -391,26 +486,21 @@ int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t
   const size_t W = (size_t)ctx->g.W, H = (size_t)ctx->g.H;
   // pairs are contiguous on the host (stride W) and on the device (pitch): one copy per frame
   // set -- linear when the device pitch equals the width (no per-row DMA descriptors), 2-D otherwise
+  cudaError_t e;
   if (ctx->pitch == W) {
-    ME_CUDA(ctx, cudaMemcpyAsync(s.d_cur, cur, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream));
-    ME_CUDA(ctx, cudaMemcpyAsync(s.d_ref, ref, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream));
+    e = cudaMemcpyAsync(s.d_cur, cur, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_ref, ref, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
   } else {
-    ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs,
-                                   cudaMemcpyHostToDevice, s.stream));
-    ME_CUDA(ctx, cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs,
-                                   cudaMemcpyHostToDevice, s.stream));
+    e = cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
+  }
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(s.stream);  // the first upload may still be reading the caller's buffer
+    return fail_cuda(ctx, e, "cudaMemcpyAsync(host to device)");
   }
   me::Frames f{s.d_cur, s.d_ref, ctx->pitch, ctx->frame_bytes};
-  me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
-  rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
-  if (rc) return rc;
-  const size_t ob = (size_t)ctx->nb * (size_t)npairs * 4;
-  if (mvx) ME_CUDA(ctx, cudaMemcpyAsync(mvx, s.d_mvx, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (mvy) ME_CUDA(ctx, cudaMemcpyAsync(mvy, s.d_mvy, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (ssd) ME_CUDA(ctx, cudaMemcpyAsync(ssd, s.d_ssd, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (score) ME_CUDA(ctx, cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream));
-  s.busy = true;
-  return ME_OK;
+  return finish_submit(ctx, s, f, npairs, mvx, mvy, ssd, score);
 }
 
 int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, int nframes, int32_t *mvx,
@@ -432,16 +522,7 @@ int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, i
   // pair i: current = frame i+1, reference = frame i -- two views of the same buffer
   const int npairs = nframes - 1;
   me::Frames f{s.d_cur + ctx->frame_bytes, s.d_cur, ctx->pitch, ctx->frame_bytes};
-  me::Out o{s.d_mvx, s.d_mvy, s.d_ssd, s.d_score};
-  rc = run_search(ctx, f, npairs, 0, ctx->g.nby, o, s.stream);
-  if (rc) return rc;
-  const size_t ob = (size_t)ctx->nb * (size_t)npairs * 4;
-  if (mvx) ME_CUDA(ctx, cudaMemcpyAsync(mvx, s.d_mvx, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (mvy) ME_CUDA(ctx, cudaMemcpyAsync(mvy, s.d_mvy, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (ssd) ME_CUDA(ctx, cudaMemcpyAsync(ssd, s.d_ssd, ob, cudaMemcpyDeviceToHost, s.stream));
-  if (score) ME_CUDA(ctx, cudaMemcpyAsync(score, s.d_score, ob, cudaMemcpyDeviceToHost, s.stream));
-  s.busy = true;
-  return ME_OK;
+  return finish_submit(ctx, s, f, npairs, mvx, mvy, ssd, score);
 }
 
 int me_b200_search_sequence_u8(me_b200_ctx *ctx, const uint8_t *frames, int nframes, int32_t *mvx,
@@ -686,16 +767,119 @@ int env_device() {
   return e ? atoi(e) : 0;
 }
 
-// int -> u8 with a range check (values the reference would treat as plain ints
-// outside 0..255 cannot be represented in the 8-bit device layout)
-bool pack_u8(uint8_t *dst, const int *src, size_t n) {
-  unsigned bad = 0;
-  for (size_t i = 0; i < n; i++) {
-    unsigned v = (unsigned)src[i];
-    bad |= v;
-    dst[i] = (uint8_t)v;
+extern "C" unsigned me_pack_int_to_u8(uint8_t *dst, const int *src, size_t n);  // host/me_pack.c
+
+// Worker threads for the int -> u8 narrowing of the drop-in call (the reference keeps `int`
+// pixels, utils.c:49-53).  A frame pair is cut into row chunks; workers narrow chunk after chunk
+// into the pinned staging buffers and raise a per-chunk flag, the calling thread uploads every
+// chunk as soon as its flag is up -- so narrowing and PCIe overlap and the call costs about
+// max(narrow, upload) instead of their sum.  Workers spin for a short while after a job before
+// they go back to sleep on the condition variable, which keeps back-to-back calls (a video) cheap.
+constexpr int kMaxChunks = 32;
+
+struct PackJob {
+  const int *src[2];
+  uint8_t *dst[2];
+  size_t row_elems = 0;      // W
+  int rows = 0, nchunks = 0; // chunks per frame; chunk c of frame f = flag index 2 * c + f
+  int row0[kMaxChunks + 1];
+};
+
+class PackPool {
+ public:
+  explicit PackPool(int nthreads) {
+    for (int i = 0; i < nthreads; i++) threads_.emplace_back([this] { worker(); });
   }
-  return (bad & ~0xffu) == 0;
+  ~PackPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+  }
+  // start narrowing `job`; chunk_ready(i) turns true chunk by chunk
+  void start(const PackJob &job) {
+    job_ = job;
+    bad_.store(0, std::memory_order_relaxed);
+    next_.store(0, std::memory_order_relaxed);
+    for (int i = 0; i < 2 * job.nchunks; i++) done_[i].store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+  }
+  // the caller helps (or does everything when there are no workers), then waits for flag i
+  void wait_chunk(int i) {
+    while (!done_[i].load(std::memory_order_acquire)) {
+      if (!run_one()) cpu_relax();
+    }
+  }
+  unsigned bad_bits() const { return bad_.load(std::memory_order_acquire); }
+
+ private:
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  bool run_one() {
+    const int total = 2 * job_.nchunks;
+    const int i = next_.fetch_add(1, std::memory_order_acq_rel);
+    if (i >= total) return false;
+    const int f = i & 1, c = i >> 1;
+    const size_t off = (size_t)job_.row0[c] * job_.row_elems;
+    const size_t n = (size_t)(job_.row0[c + 1] - job_.row0[c]) * job_.row_elems;
+    const unsigned b = me_pack_int_to_u8(job_.dst[f] + off, job_.src[f] + off, n);
+    if (b & ~0xffu) bad_.fetch_or(b, std::memory_order_relaxed);
+    done_[i].store(1, std::memory_order_release);
+    return true;
+  }
+  void worker() {
+    unsigned seen = 0;
+    for (;;) {
+      // spin briefly for the next job, then sleep
+      unsigned g = gen_.load(std::memory_order_acquire);
+      for (int spin = 0; g == seen && spin < 20000; spin++) {
+        cpu_relax();
+        g = gen_.load(std::memory_order_acquire);
+      }
+      if (g == seen) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+        g = gen_.load(std::memory_order_acquire);
+      }
+      seen = g;
+      if (stop_) return;
+      while (run_one()) {
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::atomic<unsigned> gen_{0};
+  bool stop_ = false;
+  PackJob job_{};
+  std::atomic<int> next_{1 << 30};
+  std::atomic<unsigned> bad_{0};
+  std::atomic<int> done_[2 * kMaxChunks];
+};
+
+PackPool *g_pack_pool = nullptr;  // created on the first drop-in call, under g_cache_mu
+
+PackPool *pack_pool() {
+  if (!g_pack_pool) {
+    int n = (int)std::thread::hardware_concurrency() - 1;
+    if (n > 6) n = 6;
+    if (const char *e = getenv("ME_B200_PACK_THREADS")) n = atoi(e);
+    if (n < 0) n = 0;
+    if (n > 32) n = 32;
+    g_pack_pool = new (std::nothrow) PackPool(n);
+  }
+  return g_pack_pool;
 }
 }  // namespace
 
@@ -703,6 +887,8 @@ void me_b200_release_cached(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   for (int i = 0; i < g_cache_n; i++) me_b200_destroy(g_cache[i].ctx);
   g_cache_n = 0;
+  delete g_pack_pool;
+  g_pack_pool = nullptr;
 }
 
 namespace {
@@ -759,11 +945,66 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
     ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_ssd, nb * 4, cudaHostAllocDefault));
     ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_score, nb * 4, cudaHostAllocDefault));
   }
-  if (!pack_u8(ctx->h_cur, pf->frame, n) || !pack_u8(ctx->h_ref, refFrame, n)) return ME_ERR_UNSUPPORTED;
-  rc = me_b200_submit(ctx, 0, ctx->h_cur, ctx->h_ref, 1, ctx->h_mvx, ctx->h_mvy, ctx->h_ssd, ctx->h_score);
-  if (rc) return rc;
-  rc = me_b200_wait(ctx, 0);
-  if (rc) return rc;
+  // narrow + upload, chunk by chunk (see PackPool), then search and fetch the field -- all on slot 0's stream
+  me_slot &sl = ctx->slots[0];
+  if (sl.busy) return ME_ERR_STATE;
+  PackPool *pool = pack_pool();
+  if (!pool) return ME_ERR_NOMEM;
+  PackJob job;
+  job.src[0] = refFrame; job.src[1] = pf->frame;
+  job.dst[0] = ctx->h_ref; job.dst[1] = ctx->h_cur;
+  job.row_elems = (size_t)W;
+  job.rows = H;
+  {
+    // chunks of >= 256 KB (narrowed), at most 8 per frame
+    int nch = (int)(n / (256u << 10));
+    if (nch < 1) nch = 1;
+    if (nch > 8) nch = 8;
+    if (nch > H) nch = H;
+    if (const char *e = getenv("ME_B200_PACK_CHUNKS")) {
+      nch = atoi(e);
+      if (nch < 1) nch = 1;
+      if (nch > kMaxChunks) nch = kMaxChunks;
+      if (nch > H) nch = H;
+    }
+    job.nchunks = nch;
+    for (int c = 0; c <= nch; c++) job.row0[c] = (int)((long long)H * c / nch);
+  }
+  pool->start(job);
+  cudaError_t ce = cudaSuccess;
+  for (int i = 0; i < 2 * job.nchunks && ce == cudaSuccess; i++) {
+    pool->wait_chunk(i);
+    const int f = i & 1, c = i >> 1;
+    const int r0 = job.row0[c], nr = job.row0[c + 1] - r0;
+    uint8_t *d = (f == 0 ? sl.d_ref : sl.d_cur) + (size_t)r0 * ctx->pitch;
+    const uint8_t *h = job.dst[f] + (size_t)r0 * W;
+    if (ctx->pitch == (size_t)W)
+      ce = cudaMemcpyAsync(d, h, (size_t)nr * W, cudaMemcpyHostToDevice, sl.stream);
+    else
+      ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, sl.stream);
+  }
+  for (int i = 0; i < 2 * job.nchunks; i++) pool->wait_chunk(i);  // (after an error: let the workers finish)
+  rc = ME_OK;
+  if (ce != cudaSuccess) rc = fail_cuda(ctx, ce, "cudaMemcpyAsync(host to device)");
+  if (rc == ME_OK && (pool->bad_bits() & ~0xffu)) {
+    snprintf(ctx->err, 256, "pixel value outside 0..255 (not representable in the 8-bit device layout)");
+    rc = ME_ERR_UNSUPPORTED;
+  }
+  if (rc == ME_OK) {
+    me::Frames f{sl.d_cur, sl.d_ref, ctx->pitch, ctx->frame_bytes};
+    // only the arrays the caller asked for travel back
+    rc = finish_submit(ctx, sl, f, 1, ctx->h_mvx, ctx->h_mvy, ssd ? ctx->h_ssd : nullptr,
+                       scores ? ctx->h_score : nullptr);
+    if (rc == ME_OK) rc = me_b200_wait(ctx, 0);
+  } else {
+    cudaStreamSynchronize(sl.stream);
+    (void)cudaGetLastError();
+  }
+  if (rc) {
+    // the drop-in has no context handle to ask: its callers read me_b200_last_error(NULL)
+    snprintf(g_err, 256, "%s", ctx->err);
+    return rc;
+  }
   for (int i = 0; i < pf->num_blks; i++) {
     block &b = pf->blks[i];
     b.motion_vectorX = ctx->h_mvx[i];  // populateBlkMotionVector, main.c:11-15

@@ -30,6 +30,13 @@ struct Frames {
   size_t pair_stride;
 };
 
+// Stream-ordered scratch (energy tables, SSIM statistics tables, work counters): one memory pool
+// per device, owned by this library and created on first use.  It keeps its memory between
+// launches (release threshold = max; footprint = the largest scratch any launch needed, e.g.
+// 4 B x W x rows per pair for the energy table, 8 B x W x rows per pair for the SSIM table) and
+// never touches the attributes of the device's default pool, which the host application shares.
+cudaError_t scratch_pool(cudaMemPool_t *pool);   // pool of the CURRENT device
+
 // host-side launchers (defined in the .cu files)
 cudaError_t launch_generic(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s);
 
@@ -44,6 +51,8 @@ struct TiledPlan;  // opaque: tensor maps + launch shape
 cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int max_pairs);
 void tiled_plan_destroy(TiledPlan *plan);
 unsigned long long tiled_plan_launches(const TiledPlan *plan);  // kernels launched so far
+// false after a failed launch_tiled that had not enqueued anything writing the caller's outputs yet
+bool tiled_plan_outputs_enqueued(const TiledPlan *plan);
 // Band sharding over NVLink: the next launch_tiled also stores every block's result into `peers`
 // (output arrays in peer-mapped memory); tiled_plan_fused_rows reports the block rows it covered.
 int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers);

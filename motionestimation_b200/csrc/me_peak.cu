@@ -28,7 +28,13 @@ __device__ __forceinline__ void step(uint32_t (&a)[kChains], uint32_t (&b)[kChai
     } else if (WHICH == ME_PEAK_IADD3) {
       a[c] = a[c] + b[c] + k;
     } else if (WHICH == ME_PEAK_LOP3) {
-      a[c] = (a[c] & b[c]) ^ k;
+      // explicit three-input LOP3s whose chain cannot be folded algebraically (round 1 measured an
+      // impossible 928 lanes/clk/SM here: the compiler had collapsed `(a & b) ^ k` repeated 16 times):
+      // majority and xor3 alternate, the second operand rotates over the chains
+      if (u & 1)
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(b[(c + 1) % kChains]), "r"(k));
+      else
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[c]) : "r"(b[c]), "r"(k));
     } else if (WHICH == ME_PEAK_IMAD) {
       a[c] = a[c] * b[c] + k;
     } else if (WHICH == ME_PEAK_IDP4A_IADD3) {

@@ -595,8 +595,11 @@ cudaError_t launch_ssim_tiled_pitch(const Geom &g, const Frames &f, int npairs, 
   p.by_count = by_count;
   const size_t blk_entries = (size_t)p.nbx_full * by_count;
   int2 *table = nullptr;
-  cudaError_t e = cudaMallocAsync(
-      (void **)&table, (p.table_pair_stride + blk_entries) * sizeof(int2) * (size_t)npairs + 256, s);
+  cudaMemPool_t pool = nullptr;
+  cudaError_t e = scratch_pool(&pool);
+  if (e != cudaSuccess) return e;
+  e = cudaMallocFromPoolAsync(
+      (void **)&table, (p.table_pair_stride + blk_entries) * sizeof(int2) * (size_t)npairs + 256, pool, s);
   if (e != cudaSuccess) return e;
   p.table = table;
   int2 *blk_stats = table + p.table_pair_stride * (size_t)npairs;

@@ -105,7 +105,7 @@ struct TiledParams {
   int s_bytes;            // FORM 2: tile bytes rounded up to 128
   int e_s;                // FORM 2: elements between the 4-aligned TMA origin and x0-R
   int s_y0;               // FORM 2: frame row of the table's first row
-  unsigned int inv_ndx;    // ceil(2^32 / (2R+1)): exact quotient by multiply-high for n < 2^16
+  unsigned int inv_ndx;    // ceil(2^32 / (2R+1)): exact quotient by multiply-high for n < 2^16; 0 when R = 0
   unsigned int *next_item; // global work counter of this launch (zeroed on the stream before it)
   Out out;
   // band sharding over NVLink: every published block is also stored into the output arrays of the
@@ -308,7 +308,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       const bool active = task < I.ntasks;
       task = min(task, I.ntasks - 1);
       // task = (part * ns + strip) * ndx + dx; ndx divides by multiply-high (tasks < 2^16)
-      const int row = (int)__umulhi((unsigned)task, p.inv_ndx);  // = part * ns + strip
+      // (R = 0: ndx = 1 and 2^32 / 1 does not fit the multiplier -- inv_ndx is 0 and row = task)
+      const int row = p.inv_ndx ? (int)__umulhi((unsigned)task, p.inv_ndx) : task;  // = part * ns + strip
       const int dx = task - row * ndx;        // window-relative horizontal offset, mvx = dx - R
       const int part = I.ns == 1 ? row : (int)__umulhi((unsigned)row, I.inv_ns);  // (2^32 / 1 does not fit)
       const int st = row - part * I.ns;
@@ -673,6 +674,13 @@ struct TiledPlan {
   bool fused_launch = false;  // the last search kernel launched was a peer-storing instantiation
   int form = 2;  // 2: energy table when possible, else 1 (default); 1: on-the-fly energies;
                  // 0: |a-b|^2 -- env ME_B200_FORM selects 0/1 for A/B measurements
+  // stream-ordered scratch (energy tables, work counter) comes from the library's own pool
+  // (scratch_pool): the device's default pool is shared with the host application and is left alone
+  cudaMemPool_t pool = nullptr;
+  // the last launch_tiled call enqueued work that writes the caller's outputs (false: the call failed
+  // before that, so another kernel may serve the same request)
+  bool outputs_enqueued = false;
+  char err[160] = {0};
 };
 
 static int env_form() {
@@ -713,14 +721,10 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
     delete pl;
     return e;
   }
-  {
-    // the energy tables live in stream-ordered scratch: keep the pool's memory between launches
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    (void)cudaGetLastError();
+  e = scratch_pool(&pl->pool);
+  if (e != cudaSuccess) {
+    delete pl;
+    return e;
   }
   const char *pt = getenv("ME_B200_PARTS");
   const char *ns = getenv("ME_B200_NS");
@@ -730,7 +734,9 @@ cudaError_t tiled_plan_create(TiledPlan **plan, const Geom &g, int /*max_pairs*/
   return cudaSuccess;
 }
 
-void tiled_plan_destroy(TiledPlan *plan) { delete plan; }
+void tiled_plan_destroy(TiledPlan *plan) {
+  delete plan;
+}
 
 int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers) {
   if (!plan || npeers < 0 || npeers > kMaxPeerOuts) return -1;
@@ -746,6 +752,7 @@ void tiled_plan_fused_rows(const TiledPlan *plan, int *begin, int *end) {
   *end = plan ? plan->fused_end : 0;
 }
 unsigned long long tiled_plan_launches(const TiledPlan *plan) { return plan ? plan->kernels_launched : 0; }
+bool tiled_plan_outputs_enqueued(const TiledPlan *plan) { return plan && plan->outputs_enqueued; }
 
 namespace {
 
@@ -829,7 +836,8 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   const bool peer = kPeerVariant && plan->npeer > 0;
   p.npeer = peer ? plan->npeer : 0;
   for (int q = 0; q < p.npeer; q++) p.peer[q] = plan->peer[q];
-  p.inv_ndx = (unsigned int)((0x100000000ull + (unsigned)(2 * g.R + 1) - 1) / (unsigned)(2 * g.R + 1));
+  p.inv_ndx = g.R == 0 ? 0u
+                       : (unsigned int)((0x100000000ull + (unsigned)(2 * g.R + 1) - 1) / (unsigned)(2 * g.R + 1));
   {
     const char *sk = getenv("ME_B200_SKEW");
     p.skew = sk ? atoi(sk) : 0;
@@ -850,9 +858,9 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-    static char msg[96];
-    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d, %d) wb=%d wh=%d", (int)r1, (int)r2, p.wb, p.wh);
-    *err = msg;
+    snprintf(plan->err, sizeof plan->err, "cuTensorMapEncodeTiled failed (%d, %d) wb=%d wh=%d", (int)r1, (int)r2,
+             p.wb, p.wh);
+    *err = plan->err;
     return cudaErrorInvalidValue;
   }
   // FORM 2: build the energy tables for the rows this launch needs (stream-ordered scratch)
@@ -870,7 +878,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     const bool has_half = by_begin + by_count > full_rows;  // the bottom row of height BH/2
     const int nhalf = has_half ? g.R + 1 : 0;
     const size_t per_pair = (size_t)tp * (size_t)(nfull + nhalf);
-    cudaError_t e = cudaMallocAsync((void **)&d_s, per_pair * 4 * (size_t)npairs + 256, s);
+    cudaError_t e = cudaMallocFromPoolAsync((void **)&d_s, per_pair * 4 * (size_t)npairs + 256, plan->pool, s);
     if (e != cudaSuccess) { *err = "cudaMallocAsync(energy table)"; return e; }
     const size_t ref_pair_stride = npairs > 1 ? f.pair_stride : f.pitch * g.H;
     if (nfull > 0) {
@@ -915,7 +923,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   // launch-wide work counter (stream-ordered scratch, zeroed on the stream)
   unsigned int *d_ctr = nullptr;
   {
-    cudaError_t ce = cudaMallocAsync((void **)&d_ctr, 256, s);
+    cudaError_t ce = cudaMallocFromPoolAsync((void **)&d_ctr, 256, plan->pool, s);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_ctr, 0, 256, s);
     if (ce != cudaSuccess) {
       *err = "cudaMallocAsync(work counter)";
@@ -945,6 +953,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   plan->kernels_launched++;
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
+  else plan->outputs_enqueued = true;
   if (e == cudaSuccess && peer) plan->fused_launch = true;
   if (d_s) cudaFreeAsync(d_s, s);
   cudaFreeAsync(d_ctr, s);
@@ -980,6 +989,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   // Block rows of full height, and (FORM 1) a bottom row of exactly half height, run tiled;
   // any other partial bottom row is a different block shape and runs on the generic kernel
   // as a one-row band.
+  plan->outputs_enqueued = false;
   const int full_rows = g.H / g.B;
   const int hrem = g.H % g.B;
   const int tiled_rows = full_rows + ((plan->form >= 1 && hrem == g.B / 2) ? 1 : 0);

@@ -12,7 +12,8 @@ from typing import Tuple
 
 import numpy as np
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+# the reference's frames/ directory (ForemanYF{1,2,4}.yuv, 352x288 luma), shipped with the package
+FRAMES_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def read_yuv_luma(path: str, width: int, height: int) -> np.ndarray:
@@ -26,7 +27,7 @@ def read_yuv_luma(path: str, width: int, height: int) -> np.ndarray:
 
 def foreman(idx: int) -> np.ndarray:
     """Shipped Foreman CIF luma frame YF<idx> (352x288), idx in {1, 2, 4}."""
-    return read_yuv_luma(os.path.join(_GOLDEN, f"ForemanYF{idx}.yuv"), 352, 288)
+    return read_yuv_luma(os.path.join(FRAMES_DIR, f"ForemanYF{idx}.yuv"), 352, 288)
 
 
 def tiled_frames(width: int, height: int, cur_idx: int = 2, ref_idx: int = 1) -> Tuple[np.ndarray, np.ndarray]:

@@ -24,6 +24,8 @@ ME_ERR_NO_DEVICE = -4
 ME_ERR_NOMEM = -5
 ME_ERR_STATE = -6
 ME_KERNEL_AUTO, ME_KERNEL_GENERIC, ME_KERNEL_TILED, ME_KERNEL_DIRECT = 0, 1, 2, 3
+ME_KERNEL_SSIM, ME_KERNEL_FAST = 4, 5
+ME_HOST_WRITE_COMBINED = 1
 ME_COST_MSE, ME_COST_SSIM = 0, 1
 ME_SEARCH_FULL, ME_SEARCH_THREE_STEP, ME_SEARCH_DIAMOND = 0, 1, 2
 ME_B200_MAX_SLOTS = 4
@@ -90,6 +92,8 @@ def load_library() -> C.CDLL:
         "me_b200_blocks_x": (C.c_int, [vp]),
         "me_b200_blocks_y": (C.c_int, [vp]),
         "me_b200_kernel_in_use": (C.c_int, [vp]),
+        "me_b200_last_kernel": (C.c_int, [vp]),
+        "me_b200_fallback_launches": (C.c_uint64, [vp]),
         "me_b200_pixel_compares": (C.c_uint64, [vp]),
         "me_b200_candidates": (C.c_uint64, [vp]),
         "me_b200_launch_count": (C.c_uint64, [vp]),
@@ -112,6 +116,7 @@ def load_library() -> C.CDLL:
         "me_b200_submit_sequence": (C.c_int, [vp, C.c_int, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_search_sequence_u8": (C.c_int, [vp, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_host_alloc": (vp, [C.c_size_t]),
+        "me_b200_host_alloc_ex": (vp, [C.c_size_t, C.c_int]),
         "me_b200_host_free": (None, [vp]),
         "me_b200_search_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int,
                                             i32p, i32p, u32p, f32p, vp]),
@@ -223,6 +228,15 @@ class Estimator:
     @property
     def kernel_in_use(self) -> int:
         return self._lib.me_b200_kernel_in_use(self._h)
+
+    @property
+    def last_kernel(self) -> int:
+        return self._lib.me_b200_last_kernel(self._h)
+
+    @property
+    def fallback_launches(self) -> int:
+        """AUTO launches the tuned kernel could not take (the generic kernel ran): 0 when all is well."""
+        return int(self._lib.me_b200_fallback_launches(self._h))
 
     @property
     def pixel_compares(self) -> int:

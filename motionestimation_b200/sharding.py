@@ -161,17 +161,31 @@ class PeerField:
 
     Layout of a copy: int32 mvx | int32 mvy | uint32 ssd | float score, each ``npairs * num_blocks``
     entries, then ``ME_B200_MAX_PEERS`` uint32 barrier flags.  The memory comes from
-    ``me_b200_device_alloc`` (exportable), the handles travel through ``all_gather_object``."""
+    ``me_b200_device_alloc`` (exportable), the handles travel through ``all_gather_object``.
 
-    def __init__(self, est, npairs: int, group=None):
+    The field is DOUBLE-BUFFERED (``copies`` = 2 by default): search k stores into buffer
+    ``k % copies`` of every rank.  One barrier per search orders "all bands have landed" but not
+    "everybody has finished reading": a rank that has passed barrier k may start search k+1 at
+    once and its stores go straight into its peers' memory.  With two buffers those stores hit the
+    buffer the peers read two searches ago; a peer can only be that far behind if its own search
+    k (which it enqueues after its reads of search k-1, in stream order) has not run, and then the
+    fast rank is still waiting in barrier k.  So the views returned for search k stay valid until
+    this rank enqueues search k+2, provided its reads are ordered before its next search on the
+    same stream (or the host synchronised in between)."""
+
+    def __init__(self, est, npairs: int, group=None, copies: int = 2):
         import torch.distributed as dist
         from .lib import Field, ME_B200_MAX_PEERS
         self.est, self.npairs, self.group = est, npairs, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > ME_B200_MAX_PEERS:
             raise ValueError("at most %d ranks" % ME_B200_MAX_PEERS)
+        if copies < 1:
+            raise ValueError("copies >= 1")
+        self.copies = copies
         self.entries = npairs * est.num_blocks
-        self.nbytes = 4 * 4 * self.entries + 256
+        self.copy_bytes = (4 * 4 * self.entries + 255) & ~255
+        self.nbytes = self.copy_bytes * copies + 256        # buffers, then the flags
         self.base = est.device_alloc(self.nbytes)
         handles = [None] * self.world
         dist.all_gather_object(handles, est.ipc_export(self.base), group=group)
@@ -184,28 +198,44 @@ class PeerField:
                 self._opened.append(p)
                 self.bases.append(p)
         a = 4 * self.entries
-        self.fields = [Field(b, b + a, b + 2 * a, b + 3 * a) for b in self.bases]
-        self.flag_ptrs = [b + 4 * a for b in self.bases]
-        self.peer_fields = [self.fields[r] for r in range(self.world) if r != self.rank]
-        self._tensors = None
+        # fields[c][r] = buffer c of rank r
+        self.fields = [[Field(b + c * self.copy_bytes, b + c * self.copy_bytes + a, b + c * self.copy_bytes + 2 * a,
+                              b + c * self.copy_bytes + 3 * a) for b in self.bases] for c in range(copies)]
+        self.flag_ptrs = [b + self.copy_bytes * copies for b in self.bases]
+        self._tensors = [None] * copies
         self.epoch = 0
         dist.barrier(group=group)    # every rank has opened every copy before anyone writes
 
-    def tensors(self):
-        """This rank's copy as torch tensors (views, no copy)."""
+    def local_field(self, c: int):
+        return self.fields[c][self.rank]
+
+    def peer_fields(self, c: int):
+        return [self.fields[c][r] for r in range(self.world) if r != self.rank]
+
+    def tensors(self, c: Optional[int] = None):
+        """Buffer `c` (default: the one the last search filled) of this rank as torch tensors (views)."""
         import torch
-        if self._tensors is None:
+        if c is None:
+            c = (self.epoch - 1) % self.copies if self.epoch else 0
+        if self._tensors[c] is None:
             shape = (self.npairs, self.est.num_blocks)
             a = 4 * self.entries
-            t = [torch.as_tensor(_RawCuda(self.base + i * a, shape, "<i4"), device="cuda") for i in range(3)]
-            sc = torch.as_tensor(_RawCuda(self.base + 3 * a, shape, "<f4"), device="cuda")
-            self._tensors = {"mvx": t[0], "mvy": t[1], "ssd": t[2], "score": sc}
-        return self._tensors
+            b = self.base + c * self.copy_bytes
+            t = [torch.as_tensor(_RawCuda(b + i * a, shape, "<i4"), device="cuda") for i in range(3)]
+            sc = torch.as_tensor(_RawCuda(b + 3 * a, shape, "<f4"), device="cuda")
+            self._tensors[c] = {"mvx": t[0], "mvy": t[1], "ssd": t[2], "score": sc}
+        return self._tensors[c]
+
+    def check(self):
+        """Synchronises the device and raises if a barrier of this context gave up waiting for a peer
+        (the field of that search is incomplete)."""
+        if self.est.peer_barrier_timed_out():
+            raise RuntimeError("peer barrier timed out: a rank did not deliver its band; the field is incomplete")
 
     def close(self):
         import torch.distributed as dist
         if self.base:
-            self._tensors = None
+            self._tensors = [None] * self.copies
             dist.barrier(group=self.group)   # nobody closes while a peer may still write
             for p in self._opened:
                 self.est.ipc_close(p)
@@ -215,15 +245,22 @@ class PeerField:
 
 
 def search_banded_peer(est, field: PeerField, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int,
-                       stream: int = 0, balance: bool = True):
+                       stream: int = 0, balance: bool = True, timeout_ms: int = 2000, check: bool = True):
     """As :func:`search_banded`, but with no collective: the rank's band is stored into every
     rank's copy of `field` by the search itself, then one device-side barrier (flags in the
-    peer-mapped memory) tells each rank that all bands have landed.  Returns views of the local copy."""
+    peer-mapped memory) tells each rank that all bands have landed.  Returns views of the local
+    buffer this search filled (see :class:`PeerField` for how long they stay valid).
+
+    `check` (default) synchronises and raises when the barrier timed out, i.e. when a peer was too
+    slow or failed and the field is incomplete.  A latency-critical caller passes ``check=False``
+    and calls ``field.check()`` before it trusts the result."""
     spans = balanced_spans(est, field.world, balance)
     b0, b1 = spans[field.rank]
-    peers = field.peer_fields
-    est.search_device_band_peers(d_cur, d_ref, pitch, pair_stride, npairs, b0, b1, field.fields[field.rank],
-                                 peers, stream)
+    c = field.epoch % field.copies
+    est.search_device_band_peers(d_cur, d_ref, pitch, pair_stride, npairs, b0, b1, field.local_field(c),
+                                 field.peer_fields(c), stream)
     field.epoch += 1
-    est.peer_barrier(field.flag_ptrs, field.rank, field.epoch, 2000, stream)
-    return field.tensors()
+    est.peer_barrier(field.flag_ptrs, field.rank, field.epoch, timeout_ms, stream)
+    if check:
+        field.check()
+    return field.tensors(c)

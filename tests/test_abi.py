@@ -42,7 +42,7 @@ def test_exports_are_plain_c():
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     for s in declared_symbols():
         assert s in exported
-    assert me.load_library().me_b200_abi_version() == 2
+    assert me.load_library().me_b200_abi_version() == 3
 
 
 def test_struct_layouts_match_reference():
@@ -104,7 +104,7 @@ def test_no_cpu_fallback_without_gpu():
 @pytest.mark.skipif(me.device_count() > 0, reason="no-GPU behaviour")
 def test_cli_fails_loudly_without_gpu(tmp_path):
     exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200")
-    g = os.path.join(ROOT, "tests", "golden")
+    g = os.path.join(ROOT, "motionestimation_b200", "data")   # the reference's frames/ directory
     p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path)],
                        capture_output=True, text=True)
     assert p.returncode == 2 and "no usable CUDA device" in p.stderr

@@ -50,11 +50,14 @@ def test_reference_arm_other_ranks_are_silent():
 
 @pytest.mark.gpu
 def test_b200_arm_line():
-    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", "4", "--no-cpu-baseline")
+    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", "4", "--no-cpu-baseline", "--sustained-s", "0.3",
+                  "--dropin-calls", "5")
     assert BASE_KEYS <= set(d) and "impl" not in d
     assert d["metric"] == "1080p_frames_per_sec_full_search_pm32" and d["unit"] == "frames/s"
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["scaling"] == "weak"
-    assert d["config"]["workload"] == "1080p_16x16_pm32" and d["config"]["kernel"] == "tiled"
+    assert d["config"]["workload"] == "1080p_16x16_pm32" and d["kernel"] == "tiled" and d["fallback_launches"] == 0
+    assert d["parity_checked"] is True and d["parity"]["blocks"] == 8160
+    assert d["e2e_dropin"]["ms_per_call"] > 0 and d["sustained"]["seconds"] > 0.2
     assert d["value"] > 1000 and d["gpu_launches"] >= 2
     r = d["roofline"]
     assert r["bound"] == "int_alu" and 0.3 < r["frac"] < 1.1 and r["peak"] > 30 and r["unit"] == "T lane-instr/s"
@@ -66,9 +69,20 @@ def test_b200_arm_line():
 @pytest.mark.gpu
 @pytest.mark.parametrize("workload,pairs", [("ssim_1080p_16x16_pm32", "4"), ("diamond_1080p_16x16_pm32", "8")])
 def test_b200_arm_widened_rows(workload, pairs):
-    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", pairs, "--no-cpu-baseline", "--workload", workload)
+    d = run_bench("--steps", "2", "--warmup", "3", "--pairs", pairs, "--no-cpu-baseline", "--workload", workload,
+                  "--sustained-s", "0.3")
+    assert d["parity_checked"] is True
     assert BASE_KEYS <= set(d) and d["config"]["workload"] == workload
     assert d["value"] > 100 and d["e2e"]["value"] > 100 and d["gpu_launches"] >= 2
     assert d["config"]["cost"] in ("mse", "ssim") and d["config"]["search"] in ("full", "three_step", "diamond")
     if d["config"]["search"] != "full":
         assert d["candidate_evaluations_per_s"] > 1e8
+
+
+def test_both_arms_build_the_same_config():
+    """The driver compares the `config` objects of the two arms: both come from workload_config()."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "foreman_8x8_pm12", "--gpus", "1")
+    assert d["config"] == bench.workload_config("foreman_8x8_pm12", 512, 1)
+    assert d["config"]["l2"] and d["config"]["parallelism"] == "frame-pair sharding x1"

@@ -102,7 +102,7 @@ def test_fast_search_1080p_device_path(orc, algo, mode):
 def test_fast_search_cli(tmp_path, orc, algo, env):
     """mes_b200 with ME_B200_SEARCH: the reference's argv, the fast pattern's field in mv_*.txt."""
     exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200")
-    g = os.path.join(ROOT, "tests", "golden")
+    g = os.path.join(ROOT, "motionestimation_b200", "data")   # the reference's frames/ directory
     p = subprocess.run([exe, f"{g}/ForemanYF2.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path)],
                        capture_output=True, text=True, env=dict(os.environ, ME_B200_SEARCH=env))
     assert p.returncode == 0, p.stderr

@@ -71,6 +71,23 @@ def test_small_span_kernels(orc, B, R, W, H, kernel):
     test_random_differential(orc, B, R, W, H, kernel)
 
 
+def test_tuned_kernel_forced_at_zero_span_on_a_wide_frame(orc):
+    """with R = 0 the multiply-high constant ceil(2^32 / (2R+1)) does not fit 32 bits; on a
+    wide frame the cost model picks several strips per item (ns > 1) and every strip but the first
+    used to publish the empty key.  ME_KERNEL_TILED + R = 0 is a public ABI option."""
+    W, H, B, R = 1920, 1080, 16, 0
+    frames = [me.tiled_frames(W, H, 2, 1), me.shifted_noise_pair(W, H, seed=3)]
+    cur = np.stack([f[0] for f in frames])
+    ref = np.stack([f[1] for f in frames])
+    for B in (16, 8):
+        with me.Estimator(W, H, B, R, max_pairs=2, kernel=me.ME_KERNEL_TILED) as est:
+            out = est.search_u8(cur, ref)
+            assert est.last_kernel == me.ME_KERNEL_TILED
+        for p in range(2):
+            o = orc.search(cur[p], ref[p], B, R)
+            check_against(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"B{B} pair {p}")
+
+
 def test_small_span_full_size(orc):
     """1080p, 16x16, +-2 (memory-bound case): the small-span kernel is what AUTO runs; equals the
     oracle on the first/last block rows and recovers a pure translation everywhere."""
@@ -147,7 +164,7 @@ def test_cli_is_byte_identical(tmp_path, args, name):
     """mes_b200: same argv, same PSNR line, same output_<B>_<R>.yuv bytes as the
     reference binary (golden md5s from results/cpu/foreman)."""
     exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200")
-    g = os.path.join(ROOT, "tests", "golden")
+    g = os.path.join(ROOT, "motionestimation_b200", "data")   # the reference's frames/ directory
     p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path), *args],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
@@ -316,14 +333,17 @@ def recompute_ssd(cur, ref, B, mvx, mvy):
     return out
 
 
-@pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 32), (1920, 1080, 16, 64), (3840, 2160, 8, 32),
-                                     (3840, 2160, 16, 32)])
+FULL_SIZES = [(1920, 1080, 16, 32), (1920, 1080, 16, 64), (3840, 2160, 8, 32), (3840, 2160, 16, 32),
+              (3840, 2160, 8, 12)]
+
+
+@pytest.mark.parametrize("W,H,B,R", FULL_SIZES)
 def test_full_size_properties(orc, W, H, B, R):
-    """BASELINE.json sizes: size-independent properties + oracle on a band.
+    """BASELINE.json sizes: size-independent properties AND the oracle on every block of the frame.
     (a) pure translation: interior blocks recover the shift with SSD 0;
     (b) the reported SSD equals the SSD recomputed from the frames at the reported MV;
-    (c) MVs stay inside the clamped window; (d) two top block rows and the bottom
-    block row equal the oracle bit for bit; (e) generic and tuned kernels agree."""
+    (c) MVs stay inside the clamped window; (d) EVERY block of both pairs (MV, SSD, score bits)
+    equals the oracle (main.c:18-82 restated, all host cores); (e) generic and tuned kernels agree."""
     rng = np.random.Generator(np.random.PCG64(W + R))
     base = rng.integers(0, 256, (H + 64, W + 64), dtype=np.uint8)
     dx, dy = 7, -5
@@ -333,6 +353,7 @@ def test_full_size_properties(orc, W, H, B, R):
     with me.Estimator(W, H, B, R, max_pairs=2) as est:
         out = est.search_u8(np.stack([cur, cur2]), np.stack([ref, ref2]))
         tuned = est.kernel_in_use
+        assert est.fallback_launches == 0
     x0, y0, w, h = me.block_grid(W, H, B)
     interior = (x0 + dx >= 0) & (y0 + dy >= 0) & (x0 + w + dx <= W) & (y0 + h + dy <= H)
     assert np.all(out["mvx"][0][interior] == dx) and np.all(out["mvy"][0][interior] == dy)
@@ -342,19 +363,58 @@ def test_full_size_properties(orc, W, H, B, R):
         assert np.all(mvx >= -np.minimum(R, x0)) and np.all(mvx <= np.minimum(R, W - w - x0))
         assert np.all(mvy >= -np.minimum(R, y0)) and np.all(mvy <= np.minimum(R, H - h - y0))
         assert np.array_equal(recompute_ssd(c, r, B, mvx, mvy), out["ssd"][p].astype(np.int64))
-    nbx = -(-W // B)
-    nb = len(x0)
-    for (b0, b1) in ((0, 2 * nbx), (nb - nbx, nb)):
-        o = orc.search(cur2, ref2, B, R, b0, b1)
-        assert np.array_equal(out["mvx"][1][b0:b1], o["mvx"]) and np.array_equal(out["mvy"][1][b0:b1], o["mvy"])
-        assert np.array_equal(out["ssd"][1][b0:b1], o["ssd"])
-        assert np.array_equal(out["score"][1][b0:b1].view(np.uint32), o["score"].view(np.uint32))
+        o = orc.search(c, r, B, R, nthreads=os.cpu_count())
+        check_against(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"{W}x{H} pair {p}")
     if tuned == me.ME_KERNEL_TILED:
         with me.Estimator(W, H, B, R, kernel=me.ME_KERNEL_GENERIC) as est:
             g = est.search_u8(cur2, ref2)
         for k in ("mvx", "mvy", "ssd"):
             assert np.array_equal(g[k][0], out[k][1]), k
         assert np.array_equal(g["score"][0].view(np.uint32), out["score"][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("W,H,B,R", FULL_SIZES)
+def test_full_frame_oracle_parity_on_bench_inputs(orc, W, H, B, R):
+    """The exact frames bench.py times (make_batch: tiled Foreman 2->1 and 4->1, shifted noise seed
+    1234 and seed 99) at the BASELINE sizes: every block of every pair -- MV, integer SSD, float
+    score bits -- against the oracle, through the device-resident entry point bench.py's `value`
+    uses (me_b200_search_device, batched).  For 1080p +-32 additionally against the UNMODIFIED
+    reference dispatch loop (main.c:144-158 via oracle/_ref, its own 100-thread pool)."""
+    torch = _torch()
+    from oracle_binding import Ref
+    frames = [me.tiled_frames(W, H, 2, 1), me.tiled_frames(W, H, 4, 1), me.shifted_noise_pair(W, H, seed=1234),
+              me.shifted_noise_pair(W, H, seed=99, shift=(-11, 7))]
+    if W > 1920:
+        frames = [frames[0], frames[2]]       # 4K: two pairs keep the CPU side of the test short
+    P = len(frames)
+    pitch = (W + 15) & ~15
+    d_cur = torch.zeros((P, H, pitch), dtype=torch.uint8, device="cuda")
+    d_ref = torch.zeros_like(d_cur)
+    d_cur[:, :, :W] = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    d_ref[:, :, :W] = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    with me.Estimator(W, H, B, R, max_pairs=P) as est:
+        nb = est.num_blocks
+        d = {k: torch.zeros((P, nb), dtype=torch.int32, device="cuda") for k in ("mvx", "mvy", "ssd")}
+        d_score = torch.zeros((P, nb), dtype=torch.float32, device="cuda")
+        est.search_device(d_cur, d_ref, pitch, H * pitch, P, d["mvx"], d["mvy"], d["ssd"], d_score)
+        torch.cuda.synchronize()
+        assert est.kernel_in_use == me.ME_KERNEL_TILED and est.fallback_launches == 0
+    out = {k: v.cpu().numpy() for k, v in d.items()}
+    out["ssd"] = out["ssd"].view(np.uint32)
+    out["score"] = d_score.cpu().numpy()
+    for p, (c, r) in enumerate(frames):
+        o = orc.search(c, r, B, R, nthreads=os.cpu_count())
+        check_against(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"{W}x{H} B{B} R{R} pair {p}")
+    if (W, H, B, R) == (1920, 1080, 16, 32) and Ref.available():
+        # the literal timed region: thpool_init(100) / runFindBestBlkMse / thpool_wait.  It keeps the MVs in
+        # the blocks and the score truncated to int (main.c:104-105); findBestBlkMse itself (called per
+        # block by Ref.search) returns the float score
+        _, o = Ref().search_pool(frames[2][0], frames[2][1], B, R)
+        assert np.array_equal(out["mvx"][2], o["mvx"]) and np.array_equal(out["mvy"][2], o["mvy"])
+        assert np.array_equal(np.trunc(out["score"][2]), o["score"])
+        o = Ref().search(frames[0][0], frames[0][1], B, R, nthreads=os.cpu_count())
+        assert np.array_equal(out["mvx"][0], o["mvx"]) and np.array_equal(out["mvy"][0], o["mvy"])
+        assert np.array_equal(out["score"][0].view(np.uint32), o["score"].view(np.uint32))
 
 
 def test_repeatability_under_load():

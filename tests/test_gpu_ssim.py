@@ -158,7 +158,7 @@ def test_ssim_cli_is_byte_identical(tmp_path, args, name):
     """mes_b200_ssim: same argv, same 'Original Score ... Compensated Score' line and the same
     output_<B>_<R>.yuv bytes as the unmodified reference program (fixtures made from it)."""
     exe = os.path.join(ROOT, "motionestimation_b200", "mes_b200_ssim")
-    g = os.path.join(ROOT, "tests", "golden")
+    g = os.path.join(ROOT, "motionestimation_b200", "data")   # the reference's frames/ directory
     p = subprocess.run([exe, f"{g}/ForemanYF4.yuv", f"{g}/ForemanYF1.yuv", str(tmp_path), *args],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr

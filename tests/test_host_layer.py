@@ -4,6 +4,7 @@ motion compensation, frame difference, PSNR."""
 import ctypes as C
 import hashlib
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -39,7 +40,7 @@ def test_block_grid_matches_oracle(W, H, B):
 
 def test_yuv_read_write_roundtrip(tmp_path):
     lib = me.load_library()
-    g = os.path.join(os.path.dirname(__file__), "golden", "ForemanYF1.yuv")
+    g = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "motionestimation_b200", "data", "ForemanYF1.yuv")
     n = 352 * 288
     buf = np.zeros(n, np.int32)
     assert lib.yuvReadFrame(g.encode(), iptr(buf), n) == 1
@@ -106,3 +107,29 @@ def test_timestamp_monotone():
     t0 = lib.getTimeStamp()
     t1 = lib.getTimeStamp()
     assert t1 >= t0 > 1.0e9
+
+
+def test_int_to_u8_narrowing_matches_numpy(tmp_path):
+    """host/me_pack.c: the narrowing of the reference's int pixels (utils.c:49-53 in reverse) at the
+    drop-in seam -- SSE2/AVX2 body + scalar tail, every length phase; returns the OR of the inputs so
+    the caller can reject pixels outside 0..255."""
+    # an internal function of libme_b200.so (not part of the ABI): compiled on its own for the test
+    src_c = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "motionestimation_b200",
+                         "host", "me_pack.c")
+    so = str(tmp_path / "me_pack.so")
+    subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src_c], check=True)
+    fn = C.CDLL(so).me_pack_int_to_u8
+    fn.restype = C.c_uint
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.Generator(np.random.PCG64(5))
+    for n in list(range(0, 70)) + [352 * 288, 1920 * 135 + 7]:
+        src = rng.integers(0, 256, n, dtype=np.int32)
+        dst = np.full(n + 8, 0xAB, np.uint8)
+        acc = fn(dst.ctypes.data, src.ctypes.data, n)
+        assert np.array_equal(dst[:n], src.astype(np.uint8)) and np.all(dst[n:] == 0xAB)
+        assert acc == (int(np.bitwise_or.reduce(src)) if n else 0)
+    for bad in (256, -1, 70000, -40000):
+        src = rng.integers(0, 256, 100, dtype=np.int32)
+        src[57] = bad
+        dst = np.zeros(100, np.uint8)
+        assert fn(dst.ctypes.data, src.ctypes.data, 100) & ~0xff

@@ -127,7 +127,7 @@ def test_ssim_oracle_vs_live_reference_random(orc, B, R, W, H, seed):
 def test_reference_ssim_binary_matches_fixture(tmp_path):
     """The stand-alone reference program, built exactly like src/cpu/run_ssim.sh:4 (no -O),
     writes the yuv and prints the scores line the fixtures hold (built -O2 in the harness)."""
-    g = os.path.join(ROOT, "tests", "golden")
+    g = os.path.join(ROOT, "motionestimation_b200", "data")   # the reference's frames/ directory
     out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "mes_ref_ssim"), os.path.join(g, "ForemanYF4.yuv"),
                           os.path.join(g, "ForemanYF1.yuv"), str(tmp_path), "16", "7", "352", "288"],
                          capture_output=True, text=True, check=True).stdout

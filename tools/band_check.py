@@ -59,7 +59,7 @@ def main():
         # (b) peer-mapped fields: no collective
         field = sharding.PeerField(est, 1)
         for _ in range(3):
-            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1)
+            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1, check=False)
         torch.cuda.synchronize()
         dist.barrier()
         tp = []
@@ -68,7 +68,7 @@ def main():
             torch.cuda.synchronize()
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             p0.record()
-            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1)
+            resp = sharding.search_banded_peer(est, field, cur, ref, W, W * H, 1, check=False)
             p1.record()
             torch.cuda.synchronize()
             tp.append(p0.elapsed_time(p1))
