@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-band-split", action="store_true")
+    ap.add_argument("--no-post", action="store_true")
     ap.add_argument("--sustained-s", type=float, default=3.0, help="length of the sustained leg (0 = skip)")
     ap.add_argument("--dropin-calls", type=int, default=50, help="me_b200_search calls of the e2e_dropin leg (0 = skip)")
     args = ap.parse_args()
@@ -637,6 +638,39 @@ def main():
                          "the library's worker threads chunk by chunk while the chunks upload, search, MVs "
                          "written into the reference's block structs"}
 
+    # ---- the stage right after the path (main.c:160-171 / utils.c:94-164), batched on the
+    # device: 5 output planes + the PSNR integers of every pair of the step's batch.  HBM-bound.
+    post = None
+    if cost == 0 and search == 0 and not args.no_post:
+        pp = min(pairs, max(1, (2 << 30) // (5 * W * H)))          # at most 2 GB of output planes
+        out5 = torch.empty((pp, 5 * H * W), dtype=torch.uint8, device="cuda")
+        sq = torch.zeros(pp, dtype=torch.int64, device="cuda")
+        mxv = torch.zeros(pp, dtype=torch.int32, device="cuda")
+        post_bytes = pp * (2 + 5) * W * H
+
+        def post_step():
+            est.postprocess_device_batch(d_cur, d_ref, pitch, H * pitch, pp, d_mvx, d_mvy, out5, 5 * W * H, sq, mxv,
+                                         stream.cuda_stream)
+        for _ in range(3):
+            post_step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            if flush is not None and post_bytes < 160 * 1024 * 1024:
+                flush.fill_(1)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            post_step()
+            p1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(p0.elapsed_time(p1))
+        pms = float(np.median(ts))
+        post = {"value": pp / (pms * 1e-3), "unit": "frames/s", "pairs": pp, "ms": pms,
+                "algorithmic_bytes": post_bytes, "achieved_gbs": post_bytes / (pms * 1e-3) / 1e9,
+                "api": "me_b200_postprocess_device_batch: ref, cur, motion-compensated, |ref-cur|, |mc-cur| planes "
+                       "+ sum (mc-cur)^2 and max pixel per pair; 2 B read + 5 B written per pixel"}
+        del out5
+
     # ---- one very large frame split by block-row bands over the ranks: NCCL gather vs
     # peer-mapped fields; every rank checks its complete field against the unsharded search
     band_split = None
@@ -728,6 +762,8 @@ def main():
                              "h2d_bytes_per_step": nslots * (slot_pairs + 1) * n,
                              "api": "me_b200_submit_sequence: pair i = frame i+1 vs frame i, each frame uploaded once"},
             "e2e_dropin": dropin,
+            "post": (dict(post, peak_gbs=hbm_peak, frac=post["achieved_gbs"] / hbm_peak, peak_source=hbm_src)
+                     if post else None),
             "sustained": sustained,
             "band_split": band_split,
             "host": {"cpus": len(all_cpus), "affinity_of_rank0": affinity,

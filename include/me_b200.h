@@ -248,6 +248,16 @@ int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
                                uint8_t *d_out5, unsigned long long *d_sq_err, uint32_t *d_max,
                                void *stream);
 
+/* batched form: pair p reads d_cur / d_ref + p*pair_stride and the p-th field (npairs*num_blocks entries,
+ * as the search writes them), writes d_out5 + p*out_pair_stride (>= 5*W*H), d_sq_err[p] and d_max[p].
+ * 16 pixels per thread (16-byte loads and stores) when W is a multiple of 16 and the buffers are
+ * 16-byte aligned; HBM-bound: 2 bytes read + 5 written per pixel. */
+int me_b200_postprocess_device_batch(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref,
+                                     size_t pitch, size_t pair_stride, int npairs,
+                                     const int32_t *d_mvx, const int32_t *d_mvy,
+                                     uint8_t *d_out5, size_t out_pair_stride,
+                                     unsigned long long *d_sq_err, uint32_t *d_max, void *stream);
+
 /* ---- integer-pipe microbenchmark (defines the roofline denominator) ---------------
  * Runs `which` (ME_PEAK_*) on `device` for about `iters` loop trips per thread
  * and returns lane-instructions per second of the named SASS op (0 on error). */

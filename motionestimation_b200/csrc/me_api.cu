@@ -42,6 +42,7 @@ struct me_b200_ctx {
   int search = ME_SEARCH_FULL;     // me_b200_set_search
   unsigned long long *d_evals = nullptr;  // fast search: candidate evaluations so far
   int *d_peer_status = nullptr;           // peer barrier: 1 after a time-out
+  cudaEvent_t band_events[32] = {nullptr}; // drop-in call: "band c has been uploaded" (created on first use)
   char err[256] = {0};
   // scratch for the int-frame drop-in path
   uint8_t *h_cur = nullptr, *h_ref = nullptr;  // pinned, W*H each
@@ -382,6 +383,8 @@ void me_b200_destroy(me_b200_ctx *ctx) {
     if (ctx->plan) me::tiled_plan_destroy(ctx->plan);
     cudaFree(ctx->d_evals);
     cudaFree(ctx->d_peer_status);
+    for (int i = 0; i < 32; i++)
+      if (ctx->band_events[i]) cudaEventDestroy(ctx->band_events[i]);
     cudaFreeHost(ctx->h_cur);
     cudaFreeHost(ctx->h_ref);
     cudaFreeHost(ctx->h_mvx);
@@ -750,6 +753,23 @@ int me_b200_postprocess_device(me_b200_ctx *ctx, const uint8_t *d_cur, const uin
   return ME_OK;
 }
 
+int me_b200_postprocess_device_batch(me_b200_ctx *ctx, const uint8_t *d_cur, const uint8_t *d_ref, size_t pitch,
+                                     size_t pair_stride, int npairs, const int32_t *d_mvx, const int32_t *d_mvy,
+                                     uint8_t *d_out5, size_t out_pair_stride, unsigned long long *d_sq_err,
+                                     uint32_t *d_max, void *stream) {
+  if (!ctx || !d_cur || !d_ref || !d_mvx || !d_mvy || !d_out5 || npairs < 1) return ME_ERR_INVALID_ARG;
+  if (pitch < (size_t)ctx->g.W) return ME_ERR_INVALID_ARG;
+  if (npairs > 1 && (pair_stride < pitch * (size_t)ctx->g.H || out_pair_stride < 5 * (size_t)ctx->g.W * ctx->g.H))
+    return ME_ERR_INVALID_ARG;
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  cudaError_t e = me::launch_postprocess_batch(ctx->g, d_cur, d_ref, pitch, pair_stride, npairs, d_mvx, d_mvy, d_out5,
+                                               out_pair_stride, d_sq_err, d_max, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_postprocess_batch");
+  ctx->launches += (uint64_t)((npairs + 65534) / 65535);
+  return ME_OK;
+}
+
 // ---- reference drop-in: int frames + predictionFrame -------------------------------
 
 namespace {
@@ -782,7 +802,7 @@ struct PackJob {
   uint8_t *dst[2];
   size_t row_elems = 0;      // W
   int rows = 0, nchunks = 0; // chunks per frame; chunk c of frame f = flag index 2 * c + f
-  int row0[kMaxChunks + 1];
+  int row0[2][kMaxChunks + 1];  // row boundaries of the chunks, per frame (0 = reference, 1 = current)
 };
 
 class PackPool {
@@ -830,9 +850,9 @@ class PackPool {
     const int i = next_.fetch_add(1, std::memory_order_acq_rel);
     if (i >= total) return false;
     const int f = i & 1, c = i >> 1;
-    const size_t off = (size_t)job_.row0[c] * job_.row_elems;
-    const size_t n = (size_t)(job_.row0[c + 1] - job_.row0[c]) * job_.row_elems;
-    const unsigned b = me_pack_int_to_u8(job_.dst[f] + off, job_.src[f] + off, n);
+    const size_t off = (size_t)job_.row0[f][c] * job_.row_elems;
+    const size_t n = (size_t)(job_.row0[f][c + 1] - job_.row0[f][c]) * job_.row_elems;
+    const unsigned b = n ? me_pack_int_to_u8(job_.dst[f] + off, job_.src[f] + off, n) : 0u;
     if (b & ~0xffu) bad_.fetch_or(b, std::memory_order_relaxed);
     done_[i].store(1, std::memory_order_release);
     return true;
@@ -945,58 +965,79 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
     ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_ssd, nb * 4, cudaHostAllocDefault));
     ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_score, nb * 4, cudaHostAllocDefault));
   }
-  // narrow + upload, chunk by chunk (see PackPool), then search and fetch the field -- all on slot 0's stream
+  // Narrow + upload + search as a pipeline over block-row BANDS of the frame: band c of the current
+  // frame and the reference rows it needs (its own rows + R below; the R rows above arrived with the
+  // band before) are narrowed by the workers (see PackPool), uploaded on the copy stream as soon as
+  // their flag is up, and band c is searched on the compute stream behind an event -- while band c+1
+  // is still being narrowed and uploaded.  The call costs about upload(first band) + search instead
+  // of narrow + upload + search.  Small frames use one band (ME_B200_DROPIN_BANDS overrides).
   me_slot &sl = ctx->slots[0];
-  if (sl.busy) return ME_ERR_STATE;
+  cudaStream_t copy_stream = ctx->slots[1].stream;
+  if (sl.busy || ctx->slots[1].busy) return ME_ERR_STATE;
   PackPool *pool = pack_pool();
   if (!pool) return ME_ERR_NOMEM;
+  int nbands = n >= (1u << 20) ? 4 : 1;
+  if (const char *e = getenv("ME_B200_DROPIN_BANDS")) nbands = atoi(e);
+  if (nbands < 1) nbands = 1;
+  if (nbands > kMaxChunks) nbands = kMaxChunks;
+  if (nbands > nby) nbands = nby;
+  if (!ctx->band_events[0]) {
+    for (int i = 0; i < kMaxChunks; i++) ME_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_events[i], cudaEventDisableTiming));
+  }
   PackJob job;
   job.src[0] = refFrame; job.src[1] = pf->frame;
   job.dst[0] = ctx->h_ref; job.dst[1] = ctx->h_cur;
   job.row_elems = (size_t)W;
   job.rows = H;
-  {
-    // chunks of >= 256 KB (narrowed), at most 8 per frame
-    int nch = (int)(n / (256u << 10));
-    if (nch < 1) nch = 1;
-    if (nch > 8) nch = 8;
-    if (nch > H) nch = H;
-    if (const char *e = getenv("ME_B200_PACK_CHUNKS")) {
-      nch = atoi(e);
-      if (nch < 1) nch = 1;
-      if (nch > kMaxChunks) nch = kMaxChunks;
-      if (nch > H) nch = H;
-    }
-    job.nchunks = nch;
-    for (int c = 0; c <= nch; c++) job.row0[c] = (int)((long long)H * c / nch);
+  job.nchunks = nbands;
+  int band_row[kMaxChunks + 1];   // block rows
+  for (int c = 0; c <= nbands; c++) {
+    band_row[c] = (int)((long long)nby * c / nbands);
+    const int y = c == nbands ? H : (band_row[c] * B < H ? band_row[c] * B : H);
+    job.row0[1][c] = y;                                                       // current frame: the band's own rows
+    job.row0[0][c] = c == 0 ? 0 : (y + extraSpan < H ? y + extraSpan : H);    // reference: + R rows of halo below
   }
+  job.row0[0][nbands] = H;
   pool->start(job);
   cudaError_t ce = cudaSuccess;
-  for (int i = 0; i < 2 * job.nchunks && ce == cudaSuccess; i++) {
-    pool->wait_chunk(i);
-    const int f = i & 1, c = i >> 1;
-    const int r0 = job.row0[c], nr = job.row0[c + 1] - r0;
-    uint8_t *d = (f == 0 ? sl.d_ref : sl.d_cur) + (size_t)r0 * ctx->pitch;
-    const uint8_t *h = job.dst[f] + (size_t)r0 * W;
-    if (ctx->pitch == (size_t)W)
-      ce = cudaMemcpyAsync(d, h, (size_t)nr * W, cudaMemcpyHostToDevice, sl.stream);
-    else
-      ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, sl.stream);
+  rc = ME_OK;
+  me::Frames fr{sl.d_cur, sl.d_ref, ctx->pitch, ctx->frame_bytes};
+  me::Out out{sl.d_mvx, sl.d_mvy, sl.d_ssd, sl.d_score};
+  for (int c = 0; c < nbands && ce == cudaSuccess && rc == ME_OK; c++) {
+    for (int f = 0; f < 2 && ce == cudaSuccess; f++) {
+      pool->wait_chunk(2 * c + f);
+      const int r0 = job.row0[f][c], nr = job.row0[f][c + 1] - r0;
+      if (nr <= 0) continue;
+      uint8_t *d = (f == 0 ? sl.d_ref : sl.d_cur) + (size_t)r0 * ctx->pitch;
+      const uint8_t *h = job.dst[f] + (size_t)r0 * W;
+      if (ctx->pitch == (size_t)W)
+        ce = cudaMemcpyAsync(d, h, (size_t)nr * W, cudaMemcpyHostToDevice, copy_stream);
+      else
+        ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, copy_stream);
+    }
+    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->band_events[c], copy_stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sl.stream, ctx->band_events[c], 0);
+    if (ce == cudaSuccess && (pool->bad_bits() & ~0xffu)) break;   // a pixel outside 0..255: no point in searching
+    if (ce == cudaSuccess) rc = run_search(ctx, fr, 1, band_row[c], band_row[c + 1], out, sl.stream);
   }
   for (int i = 0; i < 2 * job.nchunks; i++) pool->wait_chunk(i);  // (after an error: let the workers finish)
-  rc = ME_OK;
-  if (ce != cudaSuccess) rc = fail_cuda(ctx, ce, "cudaMemcpyAsync(host to device)");
+  if (rc == ME_OK && ce != cudaSuccess) rc = fail_cuda(ctx, ce, "upload (host to device)");
   if (rc == ME_OK && (pool->bad_bits() & ~0xffu)) {
     snprintf(ctx->err, 256, "pixel value outside 0..255 (not representable in the 8-bit device layout)");
     rc = ME_ERR_UNSUPPORTED;
   }
   if (rc == ME_OK) {
-    me::Frames f{sl.d_cur, sl.d_ref, ctx->pitch, ctx->frame_bytes};
     // only the arrays the caller asked for travel back
-    rc = finish_submit(ctx, sl, f, 1, ctx->h_mvx, ctx->h_mvy, ssd ? ctx->h_ssd : nullptr,
-                       scores ? ctx->h_score : nullptr);
-    if (rc == ME_OK) rc = me_b200_wait(ctx, 0);
-  } else {
+    const size_t ob = nb * 4;
+    ce = cudaMemcpyAsync(ctx->h_mvx, sl.d_mvx, ob, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(ctx->h_mvy, sl.d_mvy, ob, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess && ssd) ce = cudaMemcpyAsync(ctx->h_ssd, sl.d_ssd, ob, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess && scores) ce = cudaMemcpyAsync(ctx->h_score, sl.d_score, ob, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(sl.stream);
+    if (ce != cudaSuccess) rc = fail_cuda(ctx, ce, "download (device to host)");
+  }
+  if (rc != ME_OK) {
+    cudaStreamSynchronize(copy_stream);
     cudaStreamSynchronize(sl.stream);
     (void)cudaGetLastError();
   }

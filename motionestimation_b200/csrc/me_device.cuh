@@ -83,6 +83,13 @@ cudaError_t launch_postprocess(const Geom &g, const uint8_t *cur, const uint8_t 
                                const int32_t *mvx, const int32_t *mvy, uint8_t *out5,
                                unsigned long long *sq_err, uint32_t *mx, cudaStream_t s);
 
+// batched: pair p reads cur/ref + p*pair_stride and the p-th field, writes out5 + p*out_pair_stride and
+// sq_err[p] / mx[p]; 16 pixels per thread when the layout is 16-byte aligned, else per pixel
+cudaError_t launch_postprocess_batch(const Geom &g, const uint8_t *cur, const uint8_t *ref, size_t pitch,
+                                     size_t pair_stride, int npairs, const int32_t *mvx, const int32_t *mvy,
+                                     uint8_t *out5, size_t out_pair_stride, unsigned long long *sq_err, uint32_t *mx,
+                                     cudaStream_t s);
+
 // order-preserving float -> u32 for non-negative floats
 __device__ __forceinline__ uint32_t score_bits(float s) { return __float_as_uint(s); }
 

@@ -214,6 +214,289 @@ direct_search_kernel(Geom g, Frames f, Out o) {
   }
 }
 
+// ---- 1 <= R <= 4, 16x16 blocks, frame width a multiple of 16: the register-streaming kernel --------
+//
+// With (2R+1)^2 <= 81 candidates per block a frame pair carries only 9..81 pixel-compares per
+// input byte, so the search has to run at streaming speed: +-1 is bound by HBM, +-2 sits on both
+// roofs at once, +-4 on the integer pipes.  The kernel has no per-candidate set-up at all:
+//   * a WARP owns a vertical stripe of the frame, 32 / G block columns wide, and walks DOWN it one
+//     pixel row per step.  A lane (block column bx, dx group gi) keeps K horizontal offsets
+//     dx = gi*K - R + k and all 2R+1 vertical offsets of them as live accumulators.
+//   * rows arrive through a per-warp shared-memory ring filled by cp.async (16 bytes per lane and
+//     frame, coalesced 512-byte rows, DEPTH rows in flight per warp; the 4-byte halos left and right
+//     of the warp's span by two lanes), so each frame byte leaves HBM once (+ 2R rows per stripe).
+//   * step y: the reference row y is byte-aligned to each dx by funnel shifts and multiplied
+//     (IDP.4A.U8.U8) with the 2R+1 current rows y-R..y+R that sit in a register window -- row y of the
+//     reference is row (y - dy - y0) of the candidate dy of the block that contains current row y - dy.
+//     Exact SSD by  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref : the cross term is one IDP.4A per 4
+//     pixels; sum ref^2 of a candidate is a difference of a running prefix sum of row energies (4
+//     IDP.4A per step and dx), sum cur^2 of a block likewise (4 per step).  Candidates are ranked by
+//     t = sum ref^2 - 2 sum cur*ref (sum cur^2 is common to a block's candidates).
+//   * a candidate finishes when its current row is the last row of its block -- at most one dy per
+//     step, a warp-uniform event: key = (t + 2^24) << 7 | raster index of (dy, dx) folds into the
+//     lane's running minimum; the unsigned minimum is the reference's first strict minimum in
+//     y-major/x-minor order (main.c:53-62).  Candidates outside the clamped window (main.c:73-76)
+//     and those of blocks another stripe owns are simply not folded in.  After the block's last dy
+//     the G lanes of a block column combine by shuffle and one lane stores MV / SSD / score.
+// The loop body is one step (no unrolling: ~250 instructions), the register window moves by
+// plain MOVs on the ALU pipe, which idles otherwise: the IDP.4A stream on the FMA-heavy pipe is
+// the only saturated resource.  Instruction budget per step at +-2 (K = 5): 100 cross-term IDP.4A
+// + 24 energy IDP.4A against ~70 other instructions (the pipe issues one IDP.4A per two cycles).
+constexpr int kStreamWarps = 4;
+constexpr uint32_t kTBias = 1u << 24;
+
+struct StreamParams {
+  int sb;           // block rows per stripe
+  int nstripes;     // stripes per pair
+  int ncg;          // column groups (= warps) per stripe
+  long long total;  // warps of work in this launch
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {   // dst: shared-window address
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int R, int K, int G, int DEPTH>
+struct StreamLayout {
+  static constexpr int ND = 2 * R + 1;
+  static constexpr int CPW = 32 / G;                 // block columns per warp
+  static constexpr int ROWB = 16 + CPW * 16 + 16;    // staged reference row: [12 pad | left halo word][own bytes][right halo word | 12 pad]
+  static constexpr int CROWB = CPW * 16;             // staged current row: own bytes only
+  static constexpr int DC = DEPTH + 2 * R;           // current rows alive at once: y-R .. y+R+DEPTH-1
+  static constexpr int kRefBytes = DEPTH * ROWB;
+  static constexpr int kCurBytes = (DC + 2 * R) * CROWB;   // + mirror of the first 2R slots, see the kernel
+  static constexpr int kWarpBytes = kRefBytes + kCurBytes;
+};
+
+template <int R, int K, int G, int DEPTH, int MINB>
+__global__ void __launch_bounds__(kStreamWarps * 32, MINB)
+stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
+  using L = StreamLayout<R, K, G, DEPTH>;
+  constexpr int ND = L::ND, CPW = L::CPW, ROWB = L::ROWB, CROWB = L::CROWB, DC = L::DC;
+  static_assert(K * G >= ND && K <= 5 && R >= 1 && R <= 4, "dx groups must cover the span");
+  extern __shared__ __align__(16) uint8_t stream_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long item = (long long)blockIdx.x * kStreamWarps + warp;
+  if (item >= sp.total) return;  // the whole warp leaves together
+  const int per_pair = sp.nstripes * sp.ncg;
+  const int pair = (int)(item / per_pair);
+  const int rem = (int)(item - (long long)pair * per_pair);
+  const int stripe = rem / sp.ncg, cg = rem - stripe * sp.ncg;
+  const int b0 = g.by_begin + stripe * sp.sb;                      // block rows [b0, b1) are this warp's
+  const int b1 = min(g.by_begin + g.by_count, b0 + sp.sb);
+  const int col = lane / G, gi = lane - col * G;
+  const int bx = cg * CPW + col;
+  const bool active = col < CPW && bx < g.nbx;
+  const int x0 = bx * 16;
+  const int H = g.H;
+  const int y_start = b0 * 16 - R;                                 // rows above the frame are skipped, not loaded
+  const int y_end = min(H - 1, b1 * 16 - 1 + R);
+  const uint8_t *cur = f.cur + (size_t)pair * f.pair_stride;
+  const uint8_t *ref = f.ref + (size_t)pair * f.pair_stride;
+  uint8_t *ring_ref = stream_smem + (size_t)warp * L::kWarpBytes;
+  uint8_t *ring_cur = ring_ref + L::kRefBytes;
+  const int ncols = min(CPW, g.nbx - cg * CPW);
+  const int xl = cg * CPW * 16 - 4, xr = (cg * CPW + ncols) * 16;  // halo words left / right of the warp's span
+
+  // horizontal clamp (main.c:73,75): candidate column x0 + dx must lie in [0, W - 16]
+  uint32_t lvalid = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int dxr = gi * K + k - R;
+    if (active && dxr <= R && x0 + dxr >= 0 && x0 + dxr + 16 <= g.W) lvalid |= 1u << k;
+  }
+  const uint32_t lane_idx = (uint32_t)(gi * K);  // raster index of the candidate = (dy+R) * ND + gi*K + k
+
+  // Producer side: everything that depends on the row is a running pointer (no multiplications in the
+  // loop: IMAD would share the FMA-heavy pipe with the IDP.4A stream).  Reference row yy_i goes to
+  // slot yy_i mod DEPTH of the reference ring, current row yy_i + R to slot mod DC of the current ring;
+  // rows above the frame (top stripe) and below the stripe's last row are not loaded.
+  // The current ring is read back 2R+1 rows at a time (the window y-R .. y+R); so that those reads
+  // are one base register + immediates, the first 2R slots are mirrored behind the last one: a
+  // window that would wrap around reads the mirror instead.
+  const ptrdiff_t pitch = (ptrdiff_t)f.pitch;
+  const uint8_t *g_ref = ref + (ptrdiff_t)y_start * pitch + x0;          // own 16 bytes of reference row yy_i
+  const uint8_t *g_cur = cur + (ptrdiff_t)(y_start + R) * pitch + x0;    // ... of current row yy_i + R
+  const uint8_t *g_halo = ref + (ptrdiff_t)y_start * pitch + (lane == 0 ? xl : xr);
+  const bool do_main = active && gi == 0;
+  const bool do_halo = (lane == 0 && xl >= 0) || (lane == 1 && xr < g.W);
+  const uint32_t s_ref = smem_addr(ring_ref) + 16 + 16 * col;
+  const uint32_t s_halo = smem_addr(ring_ref) + (lane == 0 ? 12 : 16 + 16 * ncols);
+  const uint32_t s_cur = smem_addr(ring_cur) + 16 * col;
+  int yy_i = y_start;
+  uint32_t roff_i = 0, coff_i = 0;
+  auto issue = [&]() {
+    if (yy_i <= y_end) {
+      if (do_main) {
+        if (yy_i >= 0) cp_async16(s_ref + roff_i, g_ref);
+        if (yy_i + R < H) {
+          cp_async16(s_cur + coff_i, g_cur);
+          if (coff_i < 2 * R * CROWB) cp_async16(s_cur + coff_i + DC * CROWB, g_cur);   // mirror
+        }
+      }
+      if (do_halo && yy_i >= 0) cp_async4(s_halo + roff_i, g_halo);
+    }
+    cp_async_commit();
+    g_ref += pitch; g_cur += pitch; g_halo += pitch;
+    yy_i++;
+    roff_i = roff_i + ROWB == (uint32_t)L::kRefBytes ? 0u : roff_i + ROWB;
+    coff_i = coff_i + CROWB == (uint32_t)(DC * CROWB) ? 0u : coff_i + CROWB;
+  };
+
+  uint32_t acc[K][ND];    // sum cur*ref of the live candidate of every (dx, dy)
+  uint32_t ss[K][ND];     // prefix sum of the reference row energies when that candidate started
+  uint32_t S[K];          // running prefix sum of the reference row energies per dx
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    S[k] = 0u;
+#pragma unroll
+    for (int i = 0; i < ND; i++) acc[k][i] = ss[k][i] = 0u;
+  }
+  uint32_t Sc = 0u, ScStart = 0u, A0 = 0u, A1 = 0u;  // sum cur^2: prefix, value at the block's start, finished blocks
+  uint32_t best = 0xffffffffu;
+
+  auto publish = [&](const int by) {
+    uint32_t m = best;
+    if (G == 2) m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if (G == 3) {
+      const int base = col * 3;
+      const uint32_t m0 = __shfl_sync(0xffffffffu, best, base & 31);
+      const uint32_t m1 = __shfl_sync(0xffffffffu, best, (base + 1) & 31);
+      const uint32_t m2 = __shfl_sync(0xffffffffu, best, (base + 2) & 31);
+      m = min(m0, min(m1, m2));
+    }
+    if (active && gi == 0) {
+      const int idx = (int)(m & 127u);
+      const int dyi = idx / ND, dxi = idx - dyi * ND;
+      const uint32_t a = (by & 1) ? A1 : A0;
+      const uint32_t ssd = (m >> 7) - kTBias + a;       // t + sum cur^2
+      const int hb = min(16, H - by * 16);
+      const size_t oi = (size_t)pair * g.nbx * g.nby + (size_t)by * g.nbx + bx;
+      if (o.mvx) o.mvx[oi] = dxi - R;   // main.c:58
+      if (o.mvy) o.mvy[oi] = dyi - R;   // main.c:59
+      if (o.ssd) o.ssd[oi] = ssd;
+      if (o.score) o.score[oi] = __fdiv_rn((float)ssd, (float)(16 * hb));  // main.c:27
+    }
+    best = 0xffffffffu;
+  };
+
+  // the candidates dy = di - R of all dx finish at step y: fold them in, restart their accumulators
+  auto finish = [&](const int di, const int y) {
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      if (di == d) {
+        const int dy = d - R;
+        const int c = y - dy;                       // their current row: the last row of its block
+        const int by = c >> 4, y0 = by * 16;
+        const int hb = min(16, H - y0);
+        const bool ok = by >= b0 && by < b1 && c == y0 + hb - 1 && y0 + dy >= 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const uint32_t e = S[k] - ss[k][d];                     // sum ref^2 over the candidate
+          const uint32_t t = e - acc[k][d] - acc[k][d] + kTBias;  // + 2^24 keeps it positive
+          const uint32_t key = (t << 7) + (uint32_t)(d * ND + k) + lane_idx;
+          if (ok && ((lvalid >> k) & 1u)) best = min(best, key);
+          acc[k][d] = 0u;
+          ss[k][d] = S[k];
+        }
+        // vertical clamp (main.c:74,76): the last candidate row of this block
+        if (ok && dy == min(R, H - hb - y0)) publish(by);
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (int i = 0; i < DEPTH - 1; i++) issue();
+  // consumer side: this lane's bytes of the reference slot being read / of the newest current row
+  const uint8_t *rd0 = ring_ref + 16 * col, *rd = rd0;
+  const uint8_t *cd0 = ring_cur + 16 * col;
+  uint32_t coff = 0;   // primary slot offset of the newest current row (row y + R)
+#pragma unroll 1
+  for (int y = y_start; y <= y_end; y++) {
+    __syncwarp();   // every lane has read the slots that are refilled now
+    issue();
+    cp_async_wait<DEPTH - 1>();
+    __syncwarp();   // row y of all lanes (and the halo words) has landed
+    const uint4 rv = *reinterpret_cast<const uint4 *>(rd + 16);
+    const uint32_t hl = *reinterpret_cast<const uint32_t *>(rd + 12);
+    const uint32_t hr = *reinterpret_cast<const uint32_t *>(rd + 32);
+    rd = rd + ROWB == rd0 + L::kRefBytes ? rd0 : rd + ROWB;
+    // newest current row: in the mirror when the window below it would wrap around
+    const uint8_t *cw = cd0 + (coff < 2 * R * CROWB ? coff + DC * CROWB : coff);
+    coff = coff + CROWB == (uint32_t)(DC * CROWB) ? 0u : coff + CROWB;
+    const uint32_t raw[6] = {hl, rv.x, rv.y, rv.z, rv.w, hr};   // bytes x0-4 .. x0+19 of reference row y
+    // byte-align the reference row to each of the lane's K horizontal offsets
+    uint32_t r4[K][4];
+    if (G == 1) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        constexpr int kb = 4 - R;           // + k: byte offset of dx = k - R in raw
+        const int b = kb + k, wi = b >> 2;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          r4[k][q] = (b & 3) ? __funnelshift_r(raw[wi + q], raw[wi + q + 1 > 5 ? 5 : wi + q + 1], 8u * (uint32_t)(b & 3))
+                             : raw[wi + q];
+      }
+    } else {
+      // the lane's first dx starts at byte b = gi*K - R + 4 of raw: align once, then shift by k bytes
+      const int b = gi * K - R + 4;
+      const bool up = b >= 4;
+      const uint32_t sh = 8u * (uint32_t)(b & 3);
+      uint32_t base[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const uint32_t lo = up ? raw[j + 1] : raw[j];
+        const uint32_t hi = up ? raw[j + 2 > 5 ? 5 : j + 2] : raw[j + 1];
+        base[j] = __funnelshift_r(lo, hi, sh);
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) r4[k][q] = k ? __funnelshift_r(base[q], base[q + 1], 8u * (uint32_t)k) : base[q];
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      S[k] += __dp4a(r4[k][0], r4[k][0], __dp4a(r4[k][1], r4[k][1], 0u)) +
+              __dp4a(r4[k][2], r4[k][2], __dp4a(r4[k][3], r4[k][3], 0u));
+    // current row y - dy = y + R - d against reference row y, for every dy and dx
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      const uint4 cv = *reinterpret_cast<const uint4 *>(cw - d * CROWB);
+      if (d == 0)   // the row that entered the window: its energy goes into the prefix of sum cur^2
+        Sc += __dp4a(cv.x, cv.x, __dp4a(cv.y, cv.y, 0u)) + __dp4a(cv.z, cv.z, __dp4a(cv.w, cv.w, 0u));
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        uint32_t a = acc[k][d];
+        a = __dp4a(cv.x, r4[k][0], a);
+        a = __dp4a(cv.y, r4[k][1], a);
+        a = __dp4a(cv.z, r4[k][2], a);
+        a = __dp4a(cv.w, r4[k][3], a);
+        acc[k][d] = a;
+      }
+    }
+    // ---- warp-uniform events of this step (S already includes row y: a candidate that finishes
+    // here covers rows up to y, one that starts at the next step begins after it)
+    const int tt = (y + 1 + R) & 15;            // dy = tt - R: its current row y - dy is row 15 of a block
+    if (tt < ND) finish(tt, y);
+    if ((H & 15) && y >= H - 1 - R) finish(y - (H - 1) + R, y);   // ... or the last row of a partial bottom block
+    const int yc = y + R;                       // the current row that entered: does it close a block?
+    if (yc < H && (((yc & 15) == 15) || yc == H - 1)) {
+      const uint32_t a = Sc - ScStart;
+      if ((yc >> 4) & 1) A1 = a; else A0 = a;
+      ScStart = Sc;
+    }
+  }
+}
+
 // ---- R = 0: the purely memory-bound end.  The only candidate of a block is the co-located one
 // (main.c:73-76 clamp the window to the block itself), so the search is one streaming pass over
 // both frames straight from global memory (aligned: dx = 0), VABSDIFF4 + IDP.4A.  A warp owns the
@@ -282,6 +565,59 @@ zero_span_kernel(Geom g, Frames f, Out o, int nbx_groups) {
   }
 }
 
+template <int R, int K, int G, int DEPTH, int MINB>
+cudaError_t launch_stream(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s) {
+  using L = StreamLayout<R, K, G, DEPTH>;
+  constexpr int CPW = L::CPW;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  StreamParams sp;
+  sp.ncg = (g.nbx + CPW - 1) / CPW;
+  // stripe height: as many warps as the machine holds at once (or a whole number of such waves),
+  // as few stripes as possible (each stripe re-reads 2R rows and fills its ring once)
+  const long long resident = (long long)sms * MINB * kStreamWarps;
+  long long best_cost = -1;
+  int best_sb = 1;
+  for (int sb = 1; sb <= g.by_count; sb++) {
+    const int nst = (g.by_count + sb - 1) / sb;
+    const long long total = (long long)npairs * nst * sp.ncg;
+    const long long waves = (total + resident - 1) / resident;
+    const long long cost = waves * (sb * 16 + 2 * R + DEPTH + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_sb = sb; }
+  }
+  if (const char *e = getenv("ME_B200_STREAM_SB")) {
+    const int v = atoi(e);
+    if (v >= 1) best_sb = v < g.by_count ? v : g.by_count;
+  }
+  sp.sb = best_sb;
+  sp.nstripes = (g.by_count + sp.sb - 1) / sp.sb;
+  sp.total = (long long)npairs * sp.nstripes * sp.ncg;
+  const int smem = kStreamWarps * L::kWarpBytes;
+  auto kern = stream_search_kernel<R, K, G, DEPTH, MINB>;
+  static bool attr_set = false;   // per instantiation
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const long long ctas = (sp.total + kStreamWarps - 1) / kStreamWarps;
+  kern<<<(unsigned)ctas, kStreamWarps * 32, smem, s>>>(g, f, o, sp);
+  return cudaGetLastError();
+}
+
+bool stream_supported(const Geom &g, const Frames &f, int npairs) {
+  if (g.B != 16 || g.R < 1 || g.R > 4 || g.W < 16 || (g.W & 15)) return false;
+  if ((f.pitch & 15) || (npairs > 1 && (f.pair_stride & 15))) return false;
+  if ((((uintptr_t)f.cur) | ((uintptr_t)f.ref)) & 15) return false;
+  if (getenv("ME_B200_NO_STREAM")) return false;
+  return true;
+}
+
 }  // namespace
 
 bool direct_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref) {
@@ -306,6 +642,17 @@ cudaError_t launch_direct(const Geom &g, const Frames &f, int npairs, const Out 
     if (oo.mvy) oo.mvy += off;
     if (oo.ssd) oo.ssd += off;
     if (oo.score) oo.score += off;
+    if (stream_supported(g, ff, n)) {
+      // 16x16 blocks, 1 <= R <= 4: the register-streaming kernel (K offsets per lane, G lanes per block column)
+      cudaError_t e;
+      if (g.R == 1) e = launch_stream<1, 3, 1, 6, 6>(g, ff, n, oo, s);
+      else if (g.R == 2) e = launch_stream<2, 5, 1, 6, 4>(g, ff, n, oo, s);
+      else if (g.R == 3) e = launch_stream<3, 4, 2, 8, 4>(g, ff, n, oo, s);
+      else e = launch_stream<4, 3, 3, 8, 4>(g, ff, n, oo, s);
+      if (e != cudaSuccess) return e;
+      done += n;
+      continue;
+    }
     dim3 grid((g.W + kTX - 1) / kTX, (rows_px + kTY - 1) / kTY, n);
     // R = 0 on a 16-byte aligned layout: the streaming kernel
     const bool stream_ok = g.R == 0 && (f.pitch & 15) == 0 && (f.pair_stride & 15) == 0 &&

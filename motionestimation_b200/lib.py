@@ -132,6 +132,8 @@ def load_library() -> C.CDLL:
         "me_b200_peer_barrier": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, C.c_uint32, C.c_int, vp]),
         "me_b200_peer_barrier_timed_out": (C.c_int, [vp, C.POINTER(C.c_int)]),
         "me_b200_postprocess_device": (C.c_int, [vp, u8p, u8p, C.c_size_t, i32p, i32p, u8p, vp, vp, vp]),
+        "me_b200_postprocess_device_batch": (C.c_int, [vp, u8p, u8p, C.c_size_t, C.c_size_t, C.c_int, i32p, i32p, u8p,
+                                                       C.c_size_t, vp, vp, vp]),
         "me_b200_int_peak": (C.c_double, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         # host layer (include/me_common.h)
         "createBlk": (None, [C.POINTER(Block)] + [C.c_int] * 6),
@@ -375,6 +377,18 @@ class Estimator:
         self._check(self._lib.me_b200_postprocess_device(
             self._h, p(d_cur), p(d_ref), pitch, p(d_mvx), p(d_mvy), p(d_out5), p(d_sq_err), p(d_max),
             stream or None), "me_b200_postprocess_device")
+
+
+    def postprocess_device_batch(self, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int, d_mvx, d_mvy,
+                                 d_out5, out_pair_stride: int, d_sq_err=None, d_max=None, stream: int = 0):
+        """Post-search stage of a whole batch (main.c:160-171 per pair): 5 stacked planes + the PSNR integers."""
+        def p(x):
+            if x is None:
+                return None
+            return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+        self._check(self._lib.me_b200_postprocess_device_batch(
+            self._h, p(d_cur), p(d_ref), pitch, pair_stride, npairs, p(d_mvx), p(d_mvy), p(d_out5),
+            out_pair_stride, p(d_sq_err), p(d_max), stream or None), "me_b200_postprocess_device_batch")
 
 
 def create_prediction_frame(cur_int: np.ndarray, width: int, height: int, blk_dim: int) -> PredictionFrame:

@@ -59,6 +59,11 @@ RANDOM_GEOMS = [
     # small spans (R <= 4 runs the one-thread-per-candidate kernel), partial right/bottom blocks
     (16, 4, 80, 64), (16, 2, 100, 50), (8, 3, 70, 45), (16, 0, 64, 64), (8, 1, 16, 8), (16, 3, 300, 70),
     (8, 4, 136, 40),
+    # 16x16 blocks on widths that are multiples of 16: the register-streaming kernel (1 <= R <= 4) -- odd
+    # heights (partial bottom blocks of every size class), one / many block columns per warp, 10- and
+    # 16-column warps (R = 4 / 3), a single block, tall and narrow
+    (16, 1, 64, 33), (16, 2, 160, 47), (16, 3, 48, 31), (16, 4, 96, 24), (16, 4, 528, 40), (16, 3, 272, 64),
+    (16, 2, 16, 16), (16, 1, 16, 200), (16, 4, 48, 17), (16, 2, 1040, 20), (16, 3, 32, 36), (16, 1, 560, 18),
 ]
 
 
@@ -88,24 +93,39 @@ def test_tuned_kernel_forced_at_zero_span_on_a_wide_frame(orc):
             check_against(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"B{B} pair {p}")
 
 
-def test_small_span_full_size(orc):
-    """1080p, 16x16, +-2 (memory-bound case): the small-span kernel is what AUTO runs; equals the
-    oracle on the first/last block rows and recovers a pure translation everywhere."""
-    W, H, B, R = 1920, 1080, 16, 2
+@pytest.mark.parametrize("R", [1, 2, 3, 4])
+def test_small_span_full_size(orc, R):
+    """1080p, 16x16, +-1..+-4 (the memory-bound end): the small-span kernel is what AUTO runs; it equals
+    the oracle on every block and recovers a pure translation everywhere; a block-row band of it too."""
+    W, H, B = 1920, 1080, 16
     rng = np.random.Generator(np.random.PCG64(3))
     base = rng.integers(0, 256, (H + 8, W + 8), dtype=np.uint8)
     ref = np.ascontiguousarray(base[4:4 + H, 4:4 + W])
-    cur = np.ascontiguousarray(base[4 - 1:4 - 1 + H, 4 + 2:4 + 2 + W])   # cur(x,y) = ref(x+2, y-1)
+    sx, sy = min(2, R), -1
+    cur = np.ascontiguousarray(base[4 + sy:4 + sy + H, 4 + sx:4 + sx + W])   # cur(x,y) = ref(x+sx, y+sy)
     cur2, ref2 = me.tiled_frames(W, H)
     with me.Estimator(W, H, B, R, max_pairs=2) as est:
         assert est.kernel_in_use == me.ME_KERNEL_DIRECT
         out = est.search_u8(np.stack([cur, cur2]), np.stack([ref, ref2]))
+        assert est.last_kernel == me.ME_KERNEL_DIRECT
+        # a band of block rows through the device entry point: rows outside it stay untouched
+        torch = _torch()
+        d_cur, d_ref = torch.from_numpy(cur2).cuda(), torch.from_numpy(ref2).cuda()
+        nb = est.num_blocks
+        band = {k: torch.full((1, nb), -7, dtype=torch.int32, device="cuda") for k in ("mvx", "mvy", "ssd")}
+        est.search_device(d_cur, d_ref, W, W * H, 1, band["mvx"], band["mvy"], band["ssd"], None, 0, 11, 30)
+        torch.cuda.synchronize()
     x0, y0, w, h = me.block_grid(W, H, B)
-    interior = (x0 + 2 >= 0) & (y0 - 1 >= 0) & (x0 + w + 2 <= W) & (y0 + h - 1 <= H)
-    assert np.all(out["mvx"][0][interior] == 2) and np.all(out["mvy"][0][interior] == -1)
+    interior = (x0 + sx >= 0) & (y0 + sy >= 0) & (x0 + w + sx <= W) & (y0 + h + sy <= H)
+    assert np.all(out["mvx"][0][interior] == sx) and np.all(out["mvy"][0][interior] == sy)
     assert not out["ssd"][0][interior].any()
-    o = orc.search(cur2, ref2, B, R)
-    check_against(out, 1, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), "tiled foreman +-2")
+    o = orc.search(cur2, ref2, B, R, nthreads=os.cpu_count())
+    check_against(out, 1, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"tiled foreman +-{R}")
+    nbx = W // B
+    for k in ("mvx", "mvy", "ssd"):
+        got = band[k].cpu().numpy()[0]
+        assert np.array_equal(got[11 * nbx:30 * nbx].view(np.uint32), o[k][11 * nbx:30 * nbx].view(np.uint32)), k
+        assert np.all(got[:11 * nbx] == -7) and np.all(got[30 * nbx:] == -7)
 
 
 # tuned-kernel formulations (env ME_B200_FORM, read when the context is created): default = energy
@@ -253,6 +273,38 @@ def test_postprocess_device_matches_golden_yuv():
         mse = float(sq.item()) / (W * H)
         psnr = 20 * np.log10(float(mx.item())) - 10 * np.log10(mse)   # utils.c:157-162
         assert "%.6f" % psnr == META[name]["psnr"]
+
+
+@pytest.mark.parametrize("W,H,B,R,P", [(1920, 1080, 16, 32, 3), (352, 288, 8, 12, 5), (100, 60, 8, 4, 2), (3840, 2160, 8, 12, 2)])
+def test_postprocess_batch_matches_oracle(orc, W, H, B, R, P):
+    """Batched post-search stage (main.c:160-171 for every pair of a batch): the 5 stacked planes of
+    every pair are byte-identical to the oracle's (motionCompensatedFrame + 2 x frameDiff, utils.c:94-134),
+    the two PSNR integers give imagePSNR (utils.c:137-164) to the printed precision.  (100 x 60: a layout
+    the 16-pixel path cannot take -- the per-pixel kernel runs.)"""
+    torch = _torch()
+    frames = [me.tiled_frames(W, H, 2, 1), me.shifted_noise_pair(W, H, seed=11), me.tiled_frames(W, H, 4, 1),
+              me.random_pair(W, H, 5), me.shifted_noise_pair(W, H, seed=12, shift=(-3, 2))][:P]
+    cur = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    ref = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    with me.Estimator(W, H, B, R, max_pairs=P) as est:
+        nb = est.num_blocks
+        mvx = torch.zeros((P, nb), dtype=torch.int32, device="cuda")
+        mvy = torch.zeros_like(mvx)
+        est.search_device(cur, ref, W, W * H, P, mvx, mvy)
+        out5 = torch.zeros((P, 5 * H, W), dtype=torch.uint8, device="cuda")
+        sq = torch.zeros(P, dtype=torch.int64, device="cuda")
+        mx = torch.zeros(P, dtype=torch.int32, device="cuda")
+        est.postprocess_device_batch(cur, ref, W, W * H, P, mvx, mvy, out5, 5 * W * H, sq, mx)
+        torch.cuda.synchronize()
+    got = out5.cpu().numpy()
+    for p, (c, r) in enumerate(frames):
+        o = orc.search(c, r, B, R, nthreads=os.cpu_count())
+        assert np.array_equal(mvx[p].cpu().numpy(), o["mvx"])
+        exp, psnr = orc.output5(c, r, B, o)
+        assert np.array_equal(got[p], exp), f"pair {p}: planes differ"
+        mse = float(sq[p].item()) / (W * H)
+        mine = 20 * np.log10(float(mx[p].item())) - 10 * np.log10(mse) if mse > 0 else 99.0   # utils.c:160
+        assert "%.6f" % mine == "%.6f" % psnr
 
 
 def test_pipelined_submit_wait():
