@@ -802,6 +802,8 @@ struct PackJob {
   uint8_t *dst[2];
   size_t row_elems = 0;      // W
   int rows = 0, nchunks = 0; // chunks per frame; chunk c of frame f = flag index 2 * c + f
+  int sub = 1;               // every chunk is narrowed as `sub` pieces, so that all workers share the FIRST
+                             // chunk (the GPU starts when it has arrived) instead of one chunk each
   int row0[2][kMaxChunks + 1];  // row boundaries of the chunks, per frame (0 = reference, 1 = current)
 };
 
@@ -820,11 +822,13 @@ class PackPool {
     for (auto &t : threads_) t.join();
   }
   // start narrowing `job`; chunk_ready(i) turns true chunk by chunk
+  int workers() const { return (int)threads_.size(); }
   void start(const PackJob &job) {
     job_ = job;
     bad_.store(0, std::memory_order_relaxed);
     next_.store(0, std::memory_order_relaxed);
     for (int i = 0; i < 2 * job.nchunks; i++) done_[i].store(0, std::memory_order_relaxed);
+    total_ = 2 * job.nchunks * job.sub;
     {
       std::lock_guard<std::mutex> lk(mu_);
       gen_.fetch_add(1, std::memory_order_release);
@@ -833,7 +837,7 @@ class PackPool {
   }
   // the caller helps (or does everything when there are no workers), then waits for flag i
   void wait_chunk(int i) {
-    while (!done_[i].load(std::memory_order_acquire)) {
+    while (done_[i].load(std::memory_order_acquire) < job_.sub) {
       if (!run_one()) cpu_relax();
     }
   }
@@ -846,15 +850,16 @@ class PackPool {
 #endif
   }
   bool run_one() {
-    const int total = 2 * job_.nchunks;
     const int i = next_.fetch_add(1, std::memory_order_acq_rel);
-    if (i >= total) return false;
-    const int f = i & 1, c = i >> 1;
-    const size_t off = (size_t)job_.row0[f][c] * job_.row_elems;
-    const size_t n = (size_t)(job_.row0[f][c + 1] - job_.row0[f][c]) * job_.row_elems;
+    if (i >= total_) return false;
+    // work item i = piece k of (chunk c, frame f), chunk-major so the first chunk is finished first
+    const int k = i % job_.sub, cf = i / job_.sub, f = cf & 1, c = cf >> 1;
+    const int r0 = job_.row0[f][c], nr = job_.row0[f][c + 1] - r0;
+    const int p0 = r0 + (int)((long long)nr * k / job_.sub), p1 = r0 + (int)((long long)nr * (k + 1) / job_.sub);
+    const size_t off = (size_t)p0 * job_.row_elems, n = (size_t)(p1 - p0) * job_.row_elems;
     const unsigned b = n ? me_pack_int_to_u8(job_.dst[f] + off, job_.src[f] + off, n) : 0u;
     if (b & ~0xffu) bad_.fetch_or(b, std::memory_order_relaxed);
-    done_[i].store(1, std::memory_order_release);
+    done_[cf].fetch_add(1, std::memory_order_release);
     return true;
   }
   void worker() {
@@ -883,6 +888,7 @@ class PackPool {
   std::atomic<unsigned> gen_{0};
   bool stop_ = false;
   PackJob job_{};
+  int total_ = 0;
   std::atomic<int> next_{1 << 30};
   std::atomic<unsigned> bad_{0};
   std::atomic<int> done_[2 * kMaxChunks];
@@ -974,6 +980,10 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   me_slot &sl = ctx->slots[0];
   cudaStream_t copy_stream = ctx->slots[1].stream;
   if (sl.busy || ctx->slots[1].busy) return ME_ERR_STATE;
+  // ME_B200_TRACE=1: phase times of this call on stderr (host clock, microseconds since entry)
+  static const bool trace = getenv("ME_B200_TRACE") != nullptr;
+  const double t_entry = trace ? getTimeStamp() : 0.0;
+  double t_band[kMaxChunks + 1] = {0}, t_launch[kMaxChunks + 1] = {0};
   PackPool *pool = pack_pool();
   if (!pool) return ME_ERR_NOMEM;
   int nbands = n >= (1u << 20) ? 4 : 1;
@@ -990,6 +1000,14 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   job.row_elems = (size_t)W;
   job.rows = H;
   job.nchunks = nbands;
+  {
+    // pieces of >= 64 KB (narrowed), one per worker + the calling thread at most
+    int sub = pool->workers() + 1;
+    const size_t band_bytes = n / (size_t)nbands;
+    if ((size_t)sub > band_bytes / (64u << 10)) sub = (int)(band_bytes / (64u << 10));
+    if (sub < 1) sub = 1;
+    job.sub = sub;
+  }
   int band_row[kMaxChunks + 1];   // block rows
   for (int c = 0; c <= nbands; c++) {
     band_row[c] = (int)((long long)nby * c / nbands);
@@ -1015,10 +1033,12 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
       else
         ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, copy_stream);
     }
+    if (trace) t_band[c] = getTimeStamp();
     if (ce == cudaSuccess) ce = cudaEventRecord(ctx->band_events[c], copy_stream);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sl.stream, ctx->band_events[c], 0);
     if (ce == cudaSuccess && (pool->bad_bits() & ~0xffu)) break;   // a pixel outside 0..255: no point in searching
     if (ce == cudaSuccess) rc = run_search(ctx, fr, 1, band_row[c], band_row[c + 1], out, sl.stream);
+    if (trace) t_launch[c] = getTimeStamp();
   }
   for (int i = 0; i < 2 * job.nchunks; i++) pool->wait_chunk(i);  // (after an error: let the workers finish)
   if (rc == ME_OK && ce != cudaSuccess) rc = fail_cuda(ctx, ce, "upload (host to device)");
@@ -1040,6 +1060,13 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
     cudaStreamSynchronize(copy_stream);
     cudaStreamSynchronize(sl.stream);
     (void)cudaGetLastError();
+  }
+  if (trace) {
+    const double t_done = getTimeStamp();
+    fprintf(stderr, "[me_b200 trace] bands %d:", nbands);
+    for (int c = 0; c < nbands; c++)
+      fprintf(stderr, " [%d up %.0f launched %.0f]", c, (t_band[c] - t_entry) * 1e6, (t_launch[c] - t_entry) * 1e6);
+    fprintf(stderr, " done %.0f us\n", (t_done - t_entry) * 1e6);
   }
   if (rc) {
     // the drop-in has no context handle to ask: its callers read me_b200_last_error(NULL)

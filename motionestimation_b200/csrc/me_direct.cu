@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "me_device.cuh"
+#include "me_tma.cuh"
 
 namespace me {
 
@@ -222,90 +223,85 @@ direct_search_kernel(Geom g, Frames f, Out o) {
 //   * a WARP owns a vertical stripe of the frame, 32 / G block columns wide, and walks DOWN it one
 //     pixel row per step.  A lane (block column bx, dx group gi) keeps K horizontal offsets
 //     dx = gi*K - R + k and all 2R+1 vertical offsets of them as live accumulators.
-//   * rows arrive through a per-warp shared-memory ring filled by cp.async (16 bytes per lane and
-//     frame, coalesced 512-byte rows, DEPTH rows in flight per warp; the 4-byte halos left and right
-//     of the warp's span by two lanes), so each frame byte leaves HBM once (+ 2R rows per stripe).
+//   * rows arrive by TMA (cp.async.bulk.tensor, u8 tensor maps over (x, y, pair)): boxes of two
+//     rows, NB boxes in flight per warp, one mbarrier per box; the reference box starts 16 bytes left
+//     of the warp's span and ends 16 bytes right of it, so the +-R halo is part of the same box and
+//     frame borders cost nothing (out-of-frame bytes are zero-filled, out-of-frame candidates are
+//     never folded in, main.c:73-76).  The warp re-arms its own ring (lane 0, every second step): no
+//     producer warp, no CTA-wide synchronisation.  Each frame byte leaves HBM once (+ 2R rows per
+//     stripe).
 //   * step y: the reference row y is byte-aligned to each dx by funnel shifts and multiplied
-//     (IDP.4A.U8.U8) with the 2R+1 current rows y-R..y+R that sit in a register window -- row y of the
-//     reference is row (y - dy - y0) of the candidate dy of the block that contains current row y - dy.
-//     Exact SSD by  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref : the cross term is one IDP.4A per 4
-//     pixels; sum ref^2 of a candidate is a difference of a running prefix sum of row energies (4
-//     IDP.4A per step and dx), sum cur^2 of a block likewise (4 per step).  Candidates are ranked by
-//     t = sum ref^2 - 2 sum cur*ref (sum cur^2 is common to a block's candidates).
+//     (IDP.4A.U8.U8) with the 2R+1 current rows y-R..y+R, read back from the ring (the first rows of
+//     the current ring are mirrored behind its end, so the window is one base register + immediates)
+//     -- row y of the reference is row (y - dy - y0) of the candidate dy of the block that contains
+//     current row y - dy.  Exact SSD by  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref : the cross
+//     term is one IDP.4A per 4 pixels; sum ref^2 of a candidate is a difference of a running prefix
+//     sum of row energies (4 IDP.4A per step and dx), sum cur^2 of a block likewise (4 per step).
+//     Candidates are ranked by t = sum ref^2 - 2 sum cur*ref (sum cur^2 is common to a block).
 //   * a candidate finishes when its current row is the last row of its block -- at most one dy per
-//     step, a warp-uniform event: key = (t + 2^24) << 7 | raster index of (dy, dx) folds into the
-//     lane's running minimum; the unsigned minimum is the reference's first strict minimum in
-//     y-major/x-minor order (main.c:53-62).  Candidates outside the clamped window (main.c:73-76)
-//     and those of blocks another stripe owns are simply not folded in.  After the block's last dy
-//     the G lanes of a block column combine by shuffle and one lane stores MV / SSD / score.
-// The loop body is one step (no unrolling: ~250 instructions), the register window moves by
-// plain MOVs on the ALU pipe, which idles otherwise: the IDP.4A stream on the FMA-heavy pipe is
-// the only saturated resource.  Instruction budget per step at +-2 (K = 5): 100 cross-term IDP.4A
-// + 24 energy IDP.4A against ~70 other instructions (the pipe issues one IDP.4A per two cycles).
-constexpr int kStreamWarps = 4;
+//     step (two next to a partial bottom block), a warp-uniform event: key = (t + 2^24) << 7 | raster
+//     index of (dy, dx) folds into the lane's running minimum; the unsigned minimum is the
+//     reference's first strict minimum in y-major/x-minor order (main.c:53-62).  Candidates outside
+//     the clamped window and those of blocks another stripe owns are simply not folded in.  After
+//     the block's last dy the G lanes of a block column combine by shuffle and one lane stores
+//     MV / SSD / score.
+// The loop body is one step; the IDP.4A stream on the FMA-heavy pipe is the only resource meant to
+// saturate.  Per step at +-2 (K = 5): 100 cross-term + 24 energy IDP.4A.
+constexpr int kStreamWarps = 1;   // one warp per CTA: everything that addresses the ring and the tensor maps is block-uniform
 constexpr uint32_t kTBias = 1u << 24;
+constexpr int kBoxRows = 2;
 
 struct StreamParams {
-  int sb;           // block rows per stripe
-  int nstripes;     // stripes per pair
+  int nstripes;     // stripes per pair: stripe i owns block rows by_begin + [i*rows/n, (i+1)*rows/n)
   int ncg;          // column groups (= warps) per stripe
   long long total;  // warps of work in this launch
 };
 
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {   // dst: shared-window address
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int R, int K, int G, int DEPTH>
+template <int R, int K, int G, int NB>
 struct StreamLayout {
   static constexpr int ND = 2 * R + 1;
   static constexpr int CPW = 32 / G;                 // block columns per warp
-  static constexpr int ROWB = 16 + CPW * 16 + 16;    // staged reference row: [12 pad | left halo word][own bytes][right halo word | 12 pad]
-  static constexpr int CROWB = CPW * 16;             // staged current row: own bytes only
-  static constexpr int DC = DEPTH + 2 * R;           // current rows alive at once: y-R .. y+R+DEPTH-1
-  static constexpr int kRefBytes = DEPTH * ROWB;
-  static constexpr int kCurBytes = (DC + 2 * R) * CROWB;   // + mirror of the first 2R slots, see the kernel
+  // staged reference row = TMA box width: 16 bytes left of the span (the last 4 of them: halo), own
+  // bytes, 16 bytes right (the first 4: halo), padded so that a two-row box is a multiple of 128 bytes
+  static constexpr int ROWB = (CPW * 16 + 32 + 63) / 64 * 64;
+  static constexpr int CROWB = (CPW * 16 + 63) / 64 * 64;        // staged current row: own bytes (+ the same padding)
+  static constexpr int MB = (2 * R + kBoxRows - 1) / kBoxRows;   // current boxes mirrored behind the ring's end
+  static constexpr int DCB = NB + MB + 1;            // current boxes alive at once
+  static constexpr int kRefBytes = NB * kBoxRows * ROWB;
+  static constexpr int kCurBytes = (DCB + MB) * kBoxRows * CROWB;
   static constexpr int kWarpBytes = kRefBytes + kCurBytes;
+  static_assert((kBoxRows * ROWB) % 128 == 0 && (kBoxRows * CROWB) % 128 == 0, "TMA destinations are 128-byte aligned");
 };
 
-template <int R, int K, int G, int DEPTH, int MINB>
+template <int R, int K, int G, int NB, int MINB>
 __global__ void __launch_bounds__(kStreamWarps * 32, MINB)
-stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
-  using L = StreamLayout<R, K, G, DEPTH>;
-  constexpr int ND = L::ND, CPW = L::CPW, ROWB = L::ROWB, CROWB = L::CROWB, DC = L::DC;
-  static_assert(K * G >= ND && K <= 5 && R >= 1 && R <= 4, "dx groups must cover the span");
-  extern __shared__ __align__(16) uint8_t stream_smem[];
+stream_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
+                     Geom g, Out o, StreamParams sp) {
+  using L = StreamLayout<R, K, G, NB>;
+  constexpr int ND = L::ND, CPW = L::CPW, ROWB = L::ROWB, CROWB = L::CROWB, DCB = L::DCB, MB = L::MB;
+  static_assert(K * G >= ND && K <= 5 && R >= 1 && R <= 4 && NB >= 2, "dx groups must cover the span");
+  extern __shared__ __align__(128) uint8_t stream_smem[];
+  __shared__ __align__(8) uint64_t bars[kStreamWarps][NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long item = (long long)blockIdx.x * kStreamWarps + warp;
-  if (item >= sp.total) return;  // the whole warp leaves together
+  if (item >= sp.total) return;  // the whole warp leaves together (no CTA-wide synchronisation below)
   const int per_pair = sp.nstripes * sp.ncg;
   const int pair = (int)(item / per_pair);
   const int rem = (int)(item - (long long)pair * per_pair);
   const int stripe = rem / sp.ncg, cg = rem - stripe * sp.ncg;
-  const int b0 = g.by_begin + stripe * sp.sb;                      // block rows [b0, b1) are this warp's
-  const int b1 = min(g.by_begin + g.by_count, b0 + sp.sb);
-  const int col = lane / G, gi = lane - col * G;
+  const int b0 = g.by_begin + (int)((long long)g.by_count * stripe / sp.nstripes);          // block rows [b0, b1)
+  const int b1 = g.by_begin + (int)((long long)g.by_count * (stripe + 1) / sp.nstripes);
+  const int col_raw = lane / G, gi = lane - col_raw * G;
+  const int col = col_raw < CPW ? col_raw : CPW - 1;               // (G = 3: lanes 30, 31 idle along on the last column)
   const int bx = cg * CPW + col;
-  const bool active = col < CPW && bx < g.nbx;
+  const bool active = col_raw < CPW && bx < g.nbx;
   const int x0 = bx * 16;
   const int H = g.H;
-  const int y_start = b0 * 16 - R;                                 // rows above the frame are skipped, not loaded
+  const int y_start = b0 * 16 - R;                                 // rows above the frame: zero-filled by TMA
   const int y_end = min(H - 1, b1 * 16 - 1 + R);
-  const uint8_t *cur = f.cur + (size_t)pair * f.pair_stride;
-  const uint8_t *ref = f.ref + (size_t)pair * f.pair_stride;
   uint8_t *ring_ref = stream_smem + (size_t)warp * L::kWarpBytes;
   uint8_t *ring_cur = ring_ref + L::kRefBytes;
-  const int ncols = min(CPW, g.nbx - cg * CPW);
-  const int xl = cg * CPW * 16 - 4, xr = (cg * CPW + ncols) * 16;  // halo words left / right of the warp's span
+  uint64_t *bar = bars[warp];
 
   // horizontal clamp (main.c:73,75): candidate column x0 + dx must lie in [0, W - 16]
   uint32_t lvalid = 0;
@@ -316,41 +312,41 @@ stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
   }
   const uint32_t lane_idx = (uint32_t)(gi * K);  // raster index of the candidate = (dy+R) * ND + gi*K + k
 
-  // Producer side: everything that depends on the row is a running pointer (no multiplications in the
-  // loop: IMAD would share the FMA-heavy pipe with the IDP.4A stream).  Reference row yy_i goes to
-  // slot yy_i mod DEPTH of the reference ring, current row yy_i + R to slot mod DC of the current ring;
-  // rows above the frame (top stripe) and below the stripe's last row are not loaded.
-  // The current ring is read back 2R+1 rows at a time (the window y-R .. y+R); so that those reads
-  // are one base register + immediates, the first 2R slots are mirrored behind the last one: a
-  // window that would wrap around reads the mirror instead.
-  const ptrdiff_t pitch = (ptrdiff_t)f.pitch;
-  const uint8_t *g_ref = ref + (ptrdiff_t)y_start * pitch + x0;          // own 16 bytes of reference row yy_i
-  const uint8_t *g_cur = cur + (ptrdiff_t)(y_start + R) * pitch + x0;    // ... of current row yy_i + R
-  const uint8_t *g_halo = ref + (ptrdiff_t)y_start * pitch + (lane == 0 ? xl : xr);
-  const bool do_main = active && gi == 0;
-  const bool do_halo = (lane == 0 && xl >= 0) || (lane == 1 && xr < g.W);
-  const uint32_t s_ref = smem_addr(ring_ref) + 16 + 16 * col;
-  const uint32_t s_halo = smem_addr(ring_ref) + (lane == 0 ? 12 : 16 + 16 * ncols);
-  const uint32_t s_cur = smem_addr(ring_cur) + 16 * col;
-  int yy_i = y_start;
-  uint32_t roff_i = 0, coff_i = 0;
-  auto issue = [&]() {
-    if (yy_i <= y_end) {
-      if (do_main) {
-        if (yy_i >= 0) cp_async16(s_ref + roff_i, g_ref);
-        if (yy_i + R < H) {
-          cp_async16(s_cur + coff_i, g_cur);
-          if (coff_i < 2 * R * CROWB) cp_async16(s_cur + coff_i + DC * CROWB, g_cur);   // mirror
-        }
-      }
-      if (do_halo && yy_i >= 0) cp_async4(s_halo + roff_i, g_halo);
+  // ---- producer: box j = reference rows y_start + 2j, +1 and current rows y_start + R + 2j, +1
+  const int nboxes = (y_end - y_start + kBoxRows) / kBoxRows;
+  const int x_span = cg * CPW * 16;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) mbar_init(&bar[j], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t s_ref = smem_u32(ring_ref), s_cur = smem_u32(ring_cur);
+  int jb_i = 0;                    // next box to load
+  int jslot_i = 0;                 // its barrier
+  uint32_t roff_i = 0, coff_i = 0; // its slots (byte offsets)
+  auto load_box = [&]() {          // lane 0 only
+    if (jb_i < nboxes) {
+      const bool mirror = coff_i < (uint32_t)(MB * kBoxRows * CROWB);
+      // order this warp's earlier generic-proxy reads of the slots before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint64_t *b = &bar[jslot_i];
+      mbar_arrive_expect_tx(b, (uint32_t)(kBoxRows * ROWB + (mirror ? 2 : 1) * kBoxRows * CROWB));
+      const int yy = y_start + kBoxRows * jb_i;
+      // (x in 4-byte words: the maps describe the frames as u32 so that a box may be wider than 256 bytes)
+      tma_load_3d_s(s_ref + roff_i, &map_ref, b, (x_span - 16) >> 2, yy, pair);
+      tma_load_3d_s(s_cur + coff_i, &map_cur, b, x_span >> 2, yy + R, pair);
+      if (mirror) tma_load_3d_s(s_cur + coff_i + DCB * kBoxRows * CROWB, &map_cur, b, x_span >> 2, yy + R, pair);
     }
-    cp_async_commit();
-    g_ref += pitch; g_cur += pitch; g_halo += pitch;
-    yy_i++;
-    roff_i = roff_i + ROWB == (uint32_t)L::kRefBytes ? 0u : roff_i + ROWB;
-    coff_i = coff_i + CROWB == (uint32_t)(DC * CROWB) ? 0u : coff_i + CROWB;
+    jb_i++;
+    jslot_i = jslot_i + 1 == NB ? 0 : jslot_i + 1;
+    roff_i = roff_i + kBoxRows * ROWB == (uint32_t)L::kRefBytes ? 0u : roff_i + kBoxRows * ROWB;
+    coff_i = coff_i + kBoxRows * CROWB == (uint32_t)(DCB * kBoxRows * CROWB) ? 0u : coff_i + kBoxRows * CROWB;
   };
+  if (lane == 0) {
+#pragma unroll 1
+    for (int j = 0; j < NB - 1; j++) load_box();
+  }
 
   uint32_t acc[K][ND];    // sum cur*ref of the live candidate of every (dx, dy)
   uint32_t ss[K][ND];     // prefix sum of the reference row energies when that candidate started
@@ -368,7 +364,7 @@ stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
     uint32_t m = best;
     if (G == 2) m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
     if (G == 3) {
-      const int base = col * 3;
+      const int base = col_raw * 3;
       const uint32_t m0 = __shfl_sync(0xffffffffu, best, base & 31);
       const uint32_t m1 = __shfl_sync(0xffffffffu, best, (base + 1) & 31);
       const uint32_t m2 = __shfl_sync(0xffffffffu, best, (base + 2) & 31);
@@ -389,50 +385,57 @@ stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
     best = 0xffffffffu;
   };
 
-  // the candidates dy = di - R of all dx finish at step y: fold them in, restart their accumulators
-  auto finish = [&](const int di, const int y) {
+  // the candidates dy = di - R of all dx finish at step y: fold them in, restart their accumulators;
+  // returns the block row to publish (its last candidate row has just finished) or -1
+  auto finish = [&](const int di, const int y) -> int {
+    const int dy = di - R;
+    const int c = y - dy;                       // their current row: the last row of its block
+    const int by = c >> 4, y0 = by * 16;
+    const int hb = min(16, H - y0);
+    const bool ok = by >= b0 && by < b1 && c == y0 + hb - 1 && y0 + dy >= 0;
+    const uint32_t okmask = ok ? lvalid : 0u;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
       if (di == d) {
-        const int dy = d - R;
-        const int c = y - dy;                       // their current row: the last row of its block
-        const int by = c >> 4, y0 = by * 16;
-        const int hb = min(16, H - y0);
-        const bool ok = by >= b0 && by < b1 && c == y0 + hb - 1 && y0 + dy >= 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
           const uint32_t e = S[k] - ss[k][d];                     // sum ref^2 over the candidate
           const uint32_t t = e - acc[k][d] - acc[k][d] + kTBias;  // + 2^24 keeps it positive
           const uint32_t key = (t << 7) + (uint32_t)(d * ND + k) + lane_idx;
-          if (ok && ((lvalid >> k) & 1u)) best = min(best, key);
+          best = min(best, ((okmask >> k) & 1u) ? key : 0xffffffffu);
           acc[k][d] = 0u;
           ss[k][d] = S[k];
         }
-        // vertical clamp (main.c:74,76): the last candidate row of this block
-        if (ok && dy == min(R, H - hb - y0)) publish(by);
       }
     }
+    // vertical clamp (main.c:74,76): dy was the last candidate row of this block
+    return (ok && dy == min(R, H - hb - y0)) ? by : -1;
   };
 
-#pragma unroll 1
-  for (int i = 0; i < DEPTH - 1; i++) issue();
-  // consumer side: this lane's bytes of the reference slot being read / of the newest current row
+  // ---- consumer: this lane's bytes of the reference row being read / of the newest current row
   const uint8_t *rd0 = ring_ref + 16 * col, *rd = rd0;
   const uint8_t *cd0 = ring_cur + 16 * col;
-  uint32_t coff = 0;   // primary slot offset of the newest current row (row y + R)
+  uint32_t coff = 0;     // primary offset of the newest current row (row y + R) in the current ring
+  uint32_t phase = 0;    // bit j: parity of the next completion of barrier j
+  int jslot = 0;
+  const bool partial_bottom = (H & 15) != 0;
 #pragma unroll 1
-  for (int y = y_start; y <= y_end; y++) {
-    __syncwarp();   // every lane has read the slots that are refilled now
-    issue();
-    cp_async_wait<DEPTH - 1>();
-    __syncwarp();   // row y of all lanes (and the halo words) has landed
+  for (int y = y_start, s = 0; y <= y_end; y++, s++) {
+    if ((s & (kBoxRows - 1)) == 0) {
+      // a new box: the slot of the box before it is free for everybody -> refill it, then wait for ours
+      __syncwarp();
+      if (lane == 0) load_box();
+      mbar_wait(&bar[jslot], (phase >> jslot) & 1u);
+      phase ^= 1u << jslot;
+      jslot = jslot + 1 == NB ? 0 : jslot + 1;
+    }
     const uint4 rv = *reinterpret_cast<const uint4 *>(rd + 16);
     const uint32_t hl = *reinterpret_cast<const uint32_t *>(rd + 12);
     const uint32_t hr = *reinterpret_cast<const uint32_t *>(rd + 32);
     rd = rd + ROWB == rd0 + L::kRefBytes ? rd0 : rd + ROWB;
     // newest current row: in the mirror when the window below it would wrap around
-    const uint8_t *cw = cd0 + (coff < 2 * R * CROWB ? coff + DC * CROWB : coff);
-    coff = coff + CROWB == (uint32_t)(DC * CROWB) ? 0u : coff + CROWB;
+    const uint8_t *cw = cd0 + (coff < 2 * R * CROWB ? coff + DCB * kBoxRows * CROWB : coff);
+    coff = coff + CROWB == (uint32_t)(DCB * kBoxRows * CROWB) ? 0u : coff + CROWB;
     const uint32_t raw[6] = {hl, rv.x, rv.y, rv.z, rv.w, hr};   // bytes x0-4 .. x0+19 of reference row y
     // byte-align the reference row to each of the lane's K horizontal offsets
     uint32_t r4[K][4];
@@ -484,10 +487,22 @@ stream_search_kernel(Geom g, Frames f, Out o, StreamParams sp) {
       }
     }
     // ---- warp-uniform events of this step (S already includes row y: a candidate that finishes
-    // here covers rows up to y, one that starts at the next step begins after it)
-    const int tt = (y + 1 + R) & 15;            // dy = tt - R: its current row y - dy is row 15 of a block
-    if (tt < ND) finish(tt, y);
-    if ((H & 15) && y >= H - 1 - R) finish(y - (H - 1) + R, y);   // ... or the last row of a partial bottom block
+    // here covers rows up to y, one that starts at the next step begins after it).  At most two
+    // candidate rows finish per step: dy = tt - R, whose current row y - dy is row 15 of a block, and
+    // -- next to a partial bottom block -- the one whose current row is the frame's last row.
+    const int tt = (y + 1 + R) & 15;
+    const int ev0 = tt < ND ? tt : -1;
+    const int ev1 = (partial_bottom && y >= H - 1 - R) ? y - (H - 1) + R : -1;
+    if (ev0 >= 0 || ev1 >= 0) {
+#pragma unroll 1
+      for (int e = 0; e < 2; e++) {
+        const int di = e == 0 ? ev0 : ev1;
+        if (di >= 0) {
+          const int by = finish(di, y);
+          if (by >= 0) publish(by);
+        }
+      }
+    }
     const int yc = y + R;                       // the current row that entered: does it close a block?
     if (yc < H && (((yc & 15) == 15) || yc == H - 1)) {
       const uint32_t a = Sc - ScStart;
@@ -565,9 +580,9 @@ zero_span_kernel(Geom g, Frames f, Out o, int nbx_groups) {
   }
 }
 
-template <int R, int K, int G, int DEPTH, int MINB>
+template <int R, int K, int G, int NB, int MINB>
 cudaError_t launch_stream(const Geom &g, const Frames &f, int npairs, const Out &o, cudaStream_t s) {
-  using L = StreamLayout<R, K, G, DEPTH>;
+  using L = StreamLayout<R, K, G, NB>;
   constexpr int CPW = L::CPW;
   static int sms = 0;
   if (!sms) {
@@ -578,27 +593,32 @@ cudaError_t launch_stream(const Geom &g, const Frames &f, int npairs, const Out 
   }
   StreamParams sp;
   sp.ncg = (g.nbx + CPW - 1) / CPW;
-  // stripe height: as many warps as the machine holds at once (or a whole number of such waves),
-  // as few stripes as possible (each stripe re-reads 2R rows and fills its ring once)
+  // Stripes per pair: every warp runs one stripe, and a launch should be a whole number of "waves" of
+  // the warps the machine holds at once -- with as few stripes as that allows, because every stripe
+  // re-reads 2R rows and fills its ring once.  Stripes are cut evenly (block rows i*n/k), so all
+  // warps of a launch finish together.
   const long long resident = (long long)sms * MINB * kStreamWarps;
   long long best_cost = -1;
-  int best_sb = 1;
-  for (int sb = 1; sb <= g.by_count; sb++) {
-    const int nst = (g.by_count + sb - 1) / sb;
-    const long long total = (long long)npairs * nst * sp.ncg;
+  int best_n = 1;
+  for (int n = 1; n <= g.by_count; n++) {
+    const int rows = (g.by_count + n - 1) / n;   // block rows of the tallest stripe
+    const long long total = (long long)npairs * n * sp.ncg;
     const long long waves = (total + resident - 1) / resident;
-    const long long cost = waves * (sb * 16 + 2 * R + DEPTH + 8);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_sb = sb; }
+    const long long cost = waves * (rows * 16 + 2 * R + 12);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_n = n; }
   }
-  if (const char *e = getenv("ME_B200_STREAM_SB")) {
+  if (const char *e = getenv("ME_B200_STREAM_STRIPES")) {
     const int v = atoi(e);
-    if (v >= 1) best_sb = v < g.by_count ? v : g.by_count;
+    if (v >= 1) best_n = v < g.by_count ? v : g.by_count;
   }
-  sp.sb = best_sb;
-  sp.nstripes = (g.by_count + sp.sb - 1) / sp.sb;
+  sp.nstripes = best_n;
   sp.total = (long long)npairs * sp.nstripes * sp.ncg;
+  CUtensorMap map_ref, map_cur;
+  if (!encode_frames_map(&map_ref, f.ref, g.W, g.H, npairs, f.pitch, f.pair_stride, L::ROWB, kBoxRows, true) ||
+      !encode_frames_map(&map_cur, f.cur, g.W, g.H, npairs, f.pitch, f.pair_stride, L::CROWB, kBoxRows, true))
+    return cudaErrorInvalidValue;
   const int smem = kStreamWarps * L::kWarpBytes;
-  auto kern = stream_search_kernel<R, K, G, DEPTH, MINB>;
+  auto kern = stream_search_kernel<R, K, G, NB, MINB>;
   static bool attr_set = false;   // per instantiation
   if (smem > 48 * 1024 && !attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -606,7 +626,7 @@ cudaError_t launch_stream(const Geom &g, const Frames &f, int npairs, const Out 
     attr_set = true;
   }
   const long long ctas = (sp.total + kStreamWarps - 1) / kStreamWarps;
-  kern<<<(unsigned)ctas, kStreamWarps * 32, smem, s>>>(g, f, o, sp);
+  kern<<<(unsigned)ctas, kStreamWarps * 32, smem, s>>>(map_ref, map_cur, g, o, sp);
   return cudaGetLastError();
 }
 
@@ -615,6 +635,7 @@ bool stream_supported(const Geom &g, const Frames &f, int npairs) {
   if ((f.pitch & 15) || (npairs > 1 && (f.pair_stride & 15))) return false;
   if ((((uintptr_t)f.cur) | ((uintptr_t)f.ref)) & 15) return false;
   if (getenv("ME_B200_NO_STREAM")) return false;
+  if (!get_encode()) return false;
   return true;
 }
 
@@ -645,10 +666,10 @@ cudaError_t launch_direct(const Geom &g, const Frames &f, int npairs, const Out 
     if (stream_supported(g, ff, n)) {
       // 16x16 blocks, 1 <= R <= 4: the register-streaming kernel (K offsets per lane, G lanes per block column)
       cudaError_t e;
-      if (g.R == 1) e = launch_stream<1, 3, 1, 6, 6>(g, ff, n, oo, s);
-      else if (g.R == 2) e = launch_stream<2, 5, 1, 6, 4>(g, ff, n, oo, s);
-      else if (g.R == 3) e = launch_stream<3, 4, 2, 8, 4>(g, ff, n, oo, s);
-      else e = launch_stream<4, 3, 3, 8, 4>(g, ff, n, oo, s);
+      if (g.R == 1) e = launch_stream<1, 3, 1, 3, 20>(g, ff, n, oo, s);
+      else if (g.R == 2) e = launch_stream<2, 5, 1, 3, 16>(g, ff, n, oo, s);
+      else if (g.R == 3) e = launch_stream<3, 4, 2, 4, 16>(g, ff, n, oo, s);
+      else e = launch_stream<4, 3, 3, 4, 16>(g, ff, n, oo, s);
       if (e != cudaSuccess) return e;
       done += n;
       continue;
