@@ -536,6 +536,55 @@ def main():
             if inflight[s]:
                 est.wait(s)
 
+    # ---- ingest routing (N > 1): not every GPU of a box has a full-speed host link (profiles/h2d_probe_r02.txt:
+    # four GPUs of this pool's 8-GPU boxes share one PCIe uplink).  Every rank measures its copy-only H2D rate
+    # with ALL ranks copying at once; a rank whose link cannot feed its kernel sends the last pairs of every
+    # submit over a peer GPU with spare link capacity and NVLink (me_b200_set_ingest_helper).
+    ingest = None
+    if world > 1 and os.environ.get("BENCH_INGEST_HELPER", "1") != "0":
+        pb = 64 << 20
+        ph = pinned((pb,), np.uint8, True)
+        ph[:] = 1
+        pt = torch.from_numpy(ph)
+        pd = torch.empty(pb, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            pd.copy_(pt, non_blocking=True)
+        sync_all()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(16):
+            pd.copy_(pt, non_blocking=True)
+        q1.record()
+        torch.cuda.synchronize()
+        my_bw = 16 * pb / (q0.elapsed_time(q1) * 1e-3) / 1e9
+        need = 2 * n * (pairs * args.steps / (dev_ms * 1e-3)) / 1e9        # GB/s this rank's kernel consumes
+        t = torch.tensor([my_bw, need], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        bw = [float(v[0].item()) for v in allv]
+        nd = [float(v[1].item()) for v in allv]
+        del pd
+        # deterministic greedy pairing, the same on every rank: most starved rank first, donor with most spare
+        frac = {r: 1.0 - 0.96 * bw[r] / nd[r] for r in range(world)}      # share of the bytes that must detour
+        spare = {r: bw[r] - 1.03 * nd[r] for r in range(world)}
+        helpers = {}
+        for r in sorted((r for r in range(world) if frac[r] > 0.0), key=lambda r: -frac[r]):
+            hp = int(np.ceil(slot_pairs * frac[r]))
+            if hp >= slot_pairs:
+                continue
+            donors = [d for d in range(world) if d != r and d not in (h[0] for h in helpers.values())
+                      and spare[d] >= hp / slot_pairs * nd[r]]
+            if donors:
+                d = max(donors, key=lambda d: spare[d])
+                helpers[r] = (d, hp)
+        if rank in helpers:
+            est.set_ingest_helper(helpers[rank][0], helpers[rank][1])     # (local rank == device index on one node)
+        ingest = {"h2d_gbs_all_ranks_copying": [round(b, 1) for b in bw], "kernel_needs_gbs": round(nd[0], 1),
+                  "helpers": {str(r): {"via_gpu": h[0], "pairs_per_submit": h[1], "of": slot_pairs}
+                              for r, h in helpers.items()},
+                  "api": "me_b200_set_ingest_helper: host -> helper GPU (its PCIe link) -> NVLink peer copy"}
+        sync_all()
+
     for _ in range(2):
         e2e_step()
     sync_all()
@@ -756,6 +805,7 @@ def main():
                            "streamed through the slot ring (upload of batch i+1 overlaps the search of batch i)"
                            % (nslots, slot_pairs),
                     "step_synchronous": e2e_sync_fps,
+                    "ingest_routing": ingest,
                     # host->device traffic the streamed run actually sustained (per GPU)
                     "h2d_gbs_per_gpu": 2 * pairs * n * (e2e_fps / world / pairs) / 1e9},
             "e2e_sequence": {"value": seq_fps, "unit": "frames/s",

@@ -32,7 +32,7 @@ extern "C" {
 
 #define ME_B200_ABI_VERSION 3 /* 2: + cost / search modes, SSIM and fast drop-ins, peer fields;
                                * 3: + me_b200_last_kernel / _fallback_launches, batched post stage,
-                               *    me_b200_host_alloc_ex (all additive) */
+                               *    me_b200_host_alloc_ex, me_b200_set_ingest_helper (all additive) */
 
 /* return codes: 0 ok, negative error.  The library never prints or exits
  * (the reference printf+exit()s, main.c:110-113,134-139; utils.c:105-108). */
@@ -163,6 +163,13 @@ int me_b200_search_u8(me_b200_ctx *ctx, const uint8_t *cur, const uint8_t *ref, 
 int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t *ref, int npairs,
                    int32_t *mvx, int32_t *mvy, uint32_t *ssd, float *score);
 int me_b200_wait(me_b200_ctx *ctx, int slot);
+/* Ingest helper for boxes whose GPUs do not all have a full-speed host link (measured on this pool's 8-GPU
+ * box, profiles/h2d_probe_r02.txt: four GPUs share one PCIe uplink and get 24 GB/s each under load, the
+ * other four 36 GB/s; a 1080p +-32 search consumes 28.4 GB/s).  After this call the LAST helper_pairs
+ * pairs of every me_b200_submit travel host -> helper_device (over THAT GPU's host link) -> this GPU
+ * (cudaMemcpyPeerAsync over NVLink), the rest directly; results are unchanged.  helper_device: any other
+ * GPU with peer access; helper_pairs < max_pairs; (-1, 0) switches it off.  Not during a submit in flight. */
+int me_b200_set_ingest_helper(me_b200_ctx *ctx, int helper_device, int helper_pairs);
 /* ---- sequences ----------------------------------------------
  * nframes consecutive frames of one video (u8, stride == width, frame i at frames + i*W*H),
  * 2 <= nframes <= max_pairs + 1.  Pair i searches frame i+1 (current) in frame i (reference),

@@ -23,6 +23,11 @@ struct me_slot {
   uint32_t *d_ssd = nullptr;
   float *d_score = nullptr;
   bool busy = false;
+  // ingest helper (me_b200_set_ingest_helper): staging for the pairs that travel over the helper GPU's
+  // host link, its stream and "upload landed" event on that device
+  uint8_t *h_cur = nullptr, *h_ref = nullptr;
+  cudaStream_t h_stream = nullptr;
+  cudaEvent_t h_event = nullptr;
 };
 
 struct me_b200_ctx {
@@ -37,6 +42,8 @@ struct me_b200_ctx {
   me::TiledPlan *plan = nullptr;
   uint64_t launches = 0;
   uint64_t fallback_launches = 0;  // AUTO searches the tuned kernel could not serve (generic kernel ran)
+  int helper_device = -1;          // ingest helper: another GPU whose host link carries part of every upload
+  int helper_pairs = 0;            // ... the last helper_pairs pairs of a submit
   int last_kernel = 0;             // kernel of the most recent search launch (0: none yet)
   int cost = ME_COST_MSE;          // me_b200_set_cost
   int search = ME_SEARCH_FULL;     // me_b200_set_search
@@ -372,6 +379,13 @@ void me_b200_destroy(me_b200_ctx *ctx) {
     for (int i = 0; i < ME_B200_MAX_SLOTS; i++) {
       me_slot &s = ctx->slots[i];
       if (s.stream) cudaStreamSynchronize(s.stream);
+      if (s.h_stream) {
+        cudaStreamSynchronize(s.h_stream);
+        cudaStreamDestroy(s.h_stream);
+      }
+      if (s.h_event) cudaEventDestroy(s.h_event);
+      cudaFree(s.h_cur);   // (helper-device memory; cudaFree takes any device's pointer)
+      cudaFree(s.h_ref);
       cudaFree(s.d_cur);
       cudaFree(s.d_ref);
       cudaFree(s.d_mvx);
@@ -489,21 +503,91 @@ int me_b200_submit(me_b200_ctx *ctx, int slot, const uint8_t *cur, const uint8_t
   const size_t W = (size_t)ctx->g.W, H = (size_t)ctx->g.H;
   // pairs are contiguous on the host (stride W) and on the device (pitch): one copy per frame
   // set -- linear when the device pitch equals the width (no per-row DMA descriptors), 2-D otherwise
-  cudaError_t e;
-  if (ctx->pitch == W) {
-    e = cudaMemcpyAsync(s.d_cur, cur, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_ref, ref, W * H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
-  } else {
-    e = cudaMemcpy2DAsync(s.d_cur, ctx->pitch, cur, W, W, H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
+  cudaError_t e = cudaSuccess;
+  // ingest helper: the last `hp` pairs go host -> helper GPU (its PCIe link) -> this GPU (NVLink peer copy)
+  int hp = ctx->helper_device >= 0 ? ctx->helper_pairs : 0;
+  if (hp > npairs - 1) hp = npairs - 1;
+  if (hp < 0) hp = 0;
+  const size_t nd = (size_t)(npairs - hp);
+  auto h2d = [&](uint8_t *dst, const uint8_t *src, size_t frames, cudaStream_t st) {
+    if (ctx->pitch == W) return cudaMemcpyAsync(dst, src, W * H * frames, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, ctx->pitch, src, W, W, H * frames, cudaMemcpyHostToDevice, st);
+  };
+  if (hp > 0) {
+    // issued first: the detour has one more hop than the direct upload
+    e = h2d(s.h_cur, cur + nd * W * H, (size_t)hp, s.h_stream);
+    if (e == cudaSuccess) e = h2d(s.h_ref, ref + nd * W * H, (size_t)hp, s.h_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(s.h_event, s.h_stream);
+  }
+  if (e == cudaSuccess) e = h2d(s.d_cur, cur, nd, s.stream);
+  if (e == cudaSuccess) e = h2d(s.d_ref, ref, nd, s.stream);
+  if (e == cudaSuccess && hp > 0) {
+    e = cudaStreamWaitEvent(s.stream, s.h_event, 0);
     if (e == cudaSuccess)
-      e = cudaMemcpy2DAsync(s.d_ref, ctx->pitch, ref, W, W, H * (size_t)npairs, cudaMemcpyHostToDevice, s.stream);
+      e = cudaMemcpyPeerAsync(s.d_cur + nd * ctx->frame_bytes, ctx->device, s.h_cur, ctx->helper_device,
+                              (size_t)hp * ctx->frame_bytes, s.stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(s.d_ref + nd * ctx->frame_bytes, ctx->device, s.h_ref, ctx->helper_device,
+                              (size_t)hp * ctx->frame_bytes, s.stream);
   }
   if (e != cudaSuccess) {
+    if (s.h_stream) cudaStreamSynchronize(s.h_stream);
     cudaStreamSynchronize(s.stream);  // the first upload may still be reading the caller's buffer
     return fail_cuda(ctx, e, "cudaMemcpyAsync(host to device)");
   }
   me::Frames f{s.d_cur, s.d_ref, ctx->pitch, ctx->frame_bytes};
   return finish_submit(ctx, s, f, npairs, mvx, mvy, ssd, score);
+}
+
+int me_b200_set_ingest_helper(me_b200_ctx *ctx, int helper_device, int helper_pairs) {
+  if (!ctx) return ME_ERR_INVALID_ARG;
+  for (int i = 0; i < ME_B200_MAX_SLOTS; i++)
+    if (ctx->slots[i].busy) return ME_ERR_STATE;
+  if (helper_device < 0 || helper_pairs <= 0) {   // switch it off (the staging stays allocated until destroy)
+    ctx->helper_device = -1;
+    ctx->helper_pairs = 0;
+    return ME_OK;
+  }
+  if (helper_device == ctx->device || helper_device >= me_b200_device_count()) return ME_ERR_INVALID_ARG;
+  if (helper_pairs >= ctx->max_pairs) return ME_ERR_INVALID_ARG;
+  if (ctx->helper_device >= 0 && ctx->helper_device != helper_device) return ME_ERR_UNSUPPORTED;   // one helper per context
+  int a = 0, b = 0;
+  ME_CUDA(ctx, cudaDeviceCanAccessPeer(&a, ctx->device, helper_device));
+  ME_CUDA(ctx, cudaDeviceCanAccessPeer(&b, helper_device, ctx->device));
+  if (!a || !b) {
+    snprintf(ctx->err, 256, "devices %d and %d cannot access each other's memory", ctx->device, helper_device);
+    return ME_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) {
+    e = cudaDeviceEnablePeerAccess(helper_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+  }
+  if (e == cudaSuccess) e = cudaSetDevice(helper_device);
+  if (e == cudaSuccess) {
+    e = cudaDeviceEnablePeerAccess(ctx->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+  }
+  const size_t bytes = ctx->frame_bytes * (size_t)helper_pairs + 256;
+  for (int i = 0; i < ME_B200_MAX_SLOTS && e == cudaSuccess; i++) {
+    me_slot &s = ctx->slots[i];
+    if (s.h_cur && helper_pairs > ctx->helper_pairs) {   // grow
+      cudaFree(s.h_cur); cudaFree(s.h_ref);
+      s.h_cur = s.h_ref = nullptr;
+    }
+    if (!s.h_cur) {
+      e = cudaMalloc(&s.h_cur, bytes);
+      if (e == cudaSuccess) e = cudaMalloc(&s.h_ref, bytes);
+    }
+    if (e == cudaSuccess && !s.h_stream) e = cudaStreamCreateWithFlags(&s.h_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !s.h_event) e = cudaEventCreateWithFlags(&s.h_event, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "me_b200_set_ingest_helper");
+  ctx->helper_device = helper_device;
+  ctx->helper_pairs = helper_pairs;
+  return ME_OK;
 }
 
 int me_b200_submit_sequence(me_b200_ctx *ctx, int slot, const uint8_t *frames, int nframes, int32_t *mvx,

@@ -70,6 +70,9 @@ namespace {
 #ifndef ME_WARPS
 #define ME_WARPS 16
 #endif
+#ifndef ME_PAIR_WARPS
+#define ME_PAIR_WARPS 16   // pair kernel: 16 warps at 128 registers (a few spilled words outside the period loop) or 12 at 168
+#endif
 constexpr int kWarps = ME_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 4;
@@ -527,6 +530,293 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------- 8x8 blocks: two block rows per item
+// tiled_pair_kernel: the same search for 8x8 blocks, but an ITEM covers TWO vertically adjacent
+// block rows and a TASK four blocks (two side by side x two on top of each other).  With 8x8
+// blocks a task of the kernel above holds only 16 IDP.4A per candidate: its per-chunk set-up (task
+// decode, current rows, the warp reduction and the shared atomics at the end) and the per-row
+// fetch are amortised over too little work -- at +-12 the kernel is issue-bound at ~50 % of peak
+// (profiles/ncu_tiled_8x8_pm12_r02_*).  Here the thread streams down ONE window column of
+// 2R + 16 rows and scores every reference row against the 8 current rows of the upper block pair
+// AND the 8 rows of the lower pair: the lower blocks' candidates simply lag the upper ones by one
+// period (candidate dy of the lower block covers reference rows 8+dy .. 15+dy), so both use the
+// same rotating-accumulator schedule, the same row fetch (5 LDS + 4 SHF per 64 IDP.4A instead of
+// per 32) and the same energy-table row (two candidates that finish at the same step cover the
+// same 8 reference rows: one LDS serves both).  A chunk carries twice the work for the same
+// set-up.  64 current words + 32 accumulators need more registers than 512 threads leave, so the
+// CTA has 12 warps (up to 168 registers per thread).
+// Only block rows whose window is not clamped vertically are paired (the two rows of an item
+// must have the same candidate rows); the few rows next to the top and bottom frame edge, an odd
+// leftover row and every geometry FORM 2 does not cover run on the kernel above.
+constexpr int kWarpsV = ME_PAIR_WARPS;
+
+__device__ __forceinline__ Item decode_item_pair(const TiledParams &p, int it) {
+  constexpr int BH = 8;
+  Item I;
+  const int per_pair = p.items_per_row * p.by_count;   // by_count: ITEM rows of this launch
+  I.pair = it / per_pair;
+  int rem = it - I.pair * per_pair;
+  const int row = rem / p.items_per_row;
+  const int ir = rem - row * p.items_per_row;
+  I.by = p.by_begin + 2 * row;                         // the upper block row
+  I.strip0 = ir * p.ns;
+  I.ns = min(p.ns, p.strips_per_row - I.strip0);
+  I.y0 = I.by * p.B;
+  I.h = BH;
+  I.dy_lo = 0;                                         // interior rows: the full 2R+1 candidate rows for both
+  I.nc = 2 * p.R + 1;
+  const int want = (I.nc + p.parts_target - 1) / p.parts_target;
+  I.m = min((want - 1 + BH - 1) / BH, (I.nc - 1) / BH);
+  const int L = I.m * BH + 1;
+  I.nparts = (I.nc + L - 1) / L;
+  I.tpp = I.ns * (2 * p.R + 1);
+  I.inv_ns = (unsigned)((0x100000000ull + (unsigned)I.ns - 1) / (unsigned)I.ns);
+  I.ntasks = I.tpp * I.nparts;
+  I.nchunks = (I.ntasks + 31) >> 5;
+  return I;
+}
+
+__global__ void __launch_bounds__(kWarpsV * 32, 1)
+tiled_pair_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
+                  const __grid_constant__ CUtensorMap map_s, const __grid_constant__ TiledParams p) {
+  constexpr int WORDS = 4, BH = 8, NSUB = 2, VS = 2;
+  constexpr int SW = 4 * WORDS, BW = SW / NSUB, WPB = WORDS / NSUB, CR = BH * VS;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ uint32_t chunk_ctr[kMaxStages];
+  __shared__ uint32_t left_ctr[kMaxStages];
+  __shared__ int item_id[kMaxStages];
+  __shared__ Item item_s[kMaxStages];
+
+  const int lane = threadIdx.x & 31;
+  const int cur_off = p.win_bytes;
+  const int s_off = p.win_bytes + p.cur_pitch * CR;
+  const int best_off = s_off + p.s_bytes;
+  const int nblk_item = p.ns * NSUB * VS;   // key slot of (strip st, vertical v, sub-block b) = (st * VS + v) * NSUB + b
+
+  auto refill = [&](const int stage) {
+    uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(p.next_item, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= p.total_items) {
+      if (lane == 0) {
+        item_id[stage] = -1;
+        mbar_arrive_expect_tx(&full_bar[stage], 0);
+      }
+      __syncwarp();
+      return;
+    }
+    const Item I = decode_item_pair(p, it);
+    for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
+    if (lane == 0) {
+      chunk_ctr[stage] = 0;
+      left_ctr[stage] = 0;
+      item_id[stage] = it;
+      item_s[stage] = I;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * CR) + (uint32_t)(p.s_pitch * p.s_rows * 4);
+      mbar_arrive_expect_tx(&full_bar[stage], bytes);
+      tma_load_3d(sb, &map_ref, &full_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
+      tma_load_3d(sb + cur_off, &map_cur, &full_bar[stage], I.strip0 * SW, I.y0, I.pair);
+      // energy tile: row k = 8-row boxes whose top reference row is y0 - R + k, k = 0 .. 2R + 8
+      tma_load_3d(sb + s_off, &map_s, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, I.y0 - p.R - p.s_y0, I.pair);
+    }
+    __syncwarp();
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; s++) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int k = 0; k < p.stages; k++) refill(k);
+
+  uint32_t dead = 0;
+  for (int k = 0; dead != (1u << p.stages) - 1u; k++) {
+    const int stage = k % p.stages;
+    if (dead & (1u << stage)) continue;
+    uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+    mbar_wait(&full_bar[stage], (k / p.stages) & 1);
+    const int it = *reinterpret_cast<volatile int *>(&item_id[stage]);
+    if (it < 0) {
+      dead |= 1u << stage;
+      continue;
+    }
+    const Item I = item_s[stage];
+    const int L = I.m * BH + 1;
+    const int ndx = 2 * p.R + 1;
+
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = (int)atomicAdd(&chunk_ctr[stage], 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= I.nchunks) break;
+
+      int task = c * 32 + lane;
+      const bool active = task < I.ntasks;
+      task = min(task, I.ntasks - 1);
+      const int row = p.inv_ndx ? (int)__umulhi((unsigned)task, p.inv_ndx) : task;  // = part * ns + strip
+      const int dx = task - row * ndx;
+      const int part = I.ns == 1 ? row : (int)__umulhi((unsigned)row, I.inv_ns);
+      const int st = row - part * I.ns;
+      const int u = p.e + st * SW + dx;
+      const uint32_t shift = 8u * (uint32_t)(u & 3);
+      const int c0 = I.nparts > 1 ? (int)(((long long)(I.nc - L) * part) / (I.nparts - 1)) : 0;
+
+      // current rows of the four blocks: rows 0..7 = upper pair, 8..15 = lower pair
+      uint32_t cur[CR][WORDS];
+      {
+        const uint4 *ct = reinterpret_cast<const uint4 *>(sb + cur_off);
+        const int pitch4 = p.cur_pitch >> 4;
+#pragma unroll
+        for (int r = 0; r < CR; r++) {
+          const uint4 v = ct[r * pitch4 + st];
+          cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
+        }
+      }
+      uint32_t acc[VS][NSUB][BH];
+      uint32_t bestk[VS][NSUB];
+#pragma unroll
+      for (int v = 0; v < VS; v++)
+#pragma unroll
+        for (int b = 0; b < NSUB; b++) bestk[v][b] = kNoKey;
+
+      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)c0 * kWinPitch) + (u >> 2);
+      constexpr int pitchw = kWinPitch >> 2;
+      const int x_strip = (I.strip0 + st) * SW;
+      int dy_fin = c0 - (BH - 1);   // dy of the UPPER candidate that finishes at step 0 of the current period
+
+      uint32_t raw[WORDS + 1];
+#pragma unroll
+      for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
+      rowp += pitchw;
+
+      const int m_uni = __reduce_max_sync(0xffffffffu, I.m);
+      const int s_pitch = p.s_pitch;
+      const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (c0 - (BH - 1)) * s_pitch + p.e_s + st * SW + dx;
+      // periods 0 .. m+1: the upper blocks ramp up in period 0 and down in period m, the lower blocks one later
+      for (int per = 0; per <= m_uni + 1; per++) {
+        const bool u_lo = per < m_uni;                      // rows r < s_: candidates that started in this period exist
+        const bool u_hi = per >= 1 && per <= m_uni;         // rows r > s_: candidates from the period before exist
+        const bool u_dg = per <= m_uni;
+        const bool l_lo = per >= 1 && per <= m_uni;
+        const bool l_hi = per >= 2;
+        const bool l_dg = per >= 1;
+#pragma unroll
+        for (int s_ = 0; s_ < BH; s_++) {
+          uint32_t ref[WORDS];
+#pragma unroll
+          for (int w = 0; w < WORDS; w++) ref[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
+#pragma unroll
+          for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
+          rowp += pitchw;
+
+          // the energy of the 8 reference rows that end at this row: shared by the upper and the lower
+          // candidate that finish now (only dereferenced when one of them exists)
+          auto group = [&](const int v, const int r) {
+            const int slot = (s_ - r + BH) % BH;
+#pragma unroll
+            for (int b = 0; b < NSUB; b++) {
+              uint32_t a = (r == 0) ? 0u : acc[v][b][slot];
+#pragma unroll
+              for (int w = 0; w < WPB; w++) a = __dp4a(cur[v * BH + r][b * WPB + w], ref[b * WPB + w], a);
+              acc[v][b][slot] = a;
+              if (r == BH - 1) {
+                const uint32_t ae = spf[b * BW];   // E + kBias8
+                uint32_t t;
+                asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %2; }" : "=r"(t) : "r"(ae), "r"(a));
+                const uint32_t key = __byte_perm(t, (uint32_t)(dy_fin + s_ - v * BH), 0x2104);
+                bestk[v][b] = min(bestk[v][b], key);
+              }
+            }
+          };
+          if (u_lo) {
+#pragma unroll
+            for (int r = 0; r < s_; r++) group(0, r);
+          }
+          if (u_hi) {
+#pragma unroll
+            for (int r = s_ + 1; r < BH; r++) group(0, r);
+          }
+          if (l_lo) {
+#pragma unroll
+            for (int r = 0; r < s_; r++) group(1, r);
+          }
+          if (l_hi) {
+#pragma unroll
+            for (int r = s_ + 1; r < BH; r++) group(1, r);
+          }
+          if (u_dg) group(0, s_);
+          if (l_dg) group(1, s_);
+          spf += s_pitch;
+        }
+        dy_fin += BH;
+      }
+
+      const unsigned peers = __match_any_sync(0xffffffffu, active ? st : -1 - lane);
+      const bool leader = (peers & (0u - peers)) == (1u << lane);
+#pragma unroll
+      for (int v = 0; v < VS; v++)
+#pragma unroll
+        for (int b = 0; b < NSUB; b++) {
+          const int x0 = x_strip + b * BW;
+          const bool ok = active && x0 < p.W && (x0 + dx - p.R >= 0) && (x0 + dx - p.R <= p.W - BW);
+          const uint32_t key = ok ? bestk[v][b] : kNoKey;
+          const uint32_t mkey = __reduce_min_sync(peers, key);
+          const uint32_t mdx = __reduce_min_sync(peers, key == mkey ? (uint32_t)dx : 0xffffu);
+          if (leader && mkey != kNoKey)
+            atomicMin(&best[(st * VS + v) * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
+        }
+    }
+    __syncwarp();
+    int prev = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      prev = (int)atomicAdd(&left_ctr[stage], 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == kWarpsV - 1) {
+      __threadfence_block();
+      for (int e = lane; e < I.ns * NSUB * VS; e += 32) {
+        const int st = e / (NSUB * VS), rem = e - st * (NSUB * VS);
+        const int v = rem / NSUB, b = rem - v * NSUB;
+        const int bx = (I.strip0 + st) * NSUB + b;
+        if (bx < p.nbx) {
+          const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[e]);
+          const uint32_t k32 = (uint32_t)(key >> 32);
+          // un-bias: ssd = t - kBias8 + sum cur^2 of this block, from the stage's current tile
+          const uint32_t *ct = reinterpret_cast<const uint32_t *>(sb + cur_off) + (v * BH) * (p.cur_pitch >> 2) +
+                               st * WORDS + b * WPB;
+          uint32_t a2 = 0;
+#pragma unroll
+          for (int r = 0; r < BH; r++)
+#pragma unroll
+            for (int w = 0; w < WPB; w++) {
+              const uint32_t x = ct[r * (p.cur_pitch >> 2) + w];
+              a2 = __dp4a(x, x, a2);
+            }
+          const uint32_t ssd = (k32 >> 8) - kBias8 + a2;
+          const size_t oi = (size_t)I.pair * p.nbx * p.nby + (size_t)(I.by + v) * p.nbx + bx;
+          if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
+          if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
+          if (p.out.ssd) p.out.ssd[oi] = ssd;
+          if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(BW * BH));  // main.c:27
+        }
+      }
+      __syncwarp();
+      refill(stage);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- FORM 2 pre-pass
 // box_energy_kernel: E(x, y) = sum of ref^2 over the bw x bh box whose top-left pixel is (x, y),
 // for table rows y = y_lo .. y_lo + nrows - 1 and all x (boxes that leave the frame read zeros and
@@ -703,24 +993,28 @@ bool tiled_plan_outputs_enqueued(const TiledPlan *plan) { return plan && plan->o
 
 namespace {
 
-template <int WORDS, int BH, int NSUB, int FORM, bool PW>
+// VS = 2: items of two block rows (tiled_pair_kernel; 8x8 blocks, FORM 2, by_count even, rows whose
+// window is not clamped vertically)
+template <int WORDS, int BH, int NSUB, int FORM, bool PW, int VS = 1>
 cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          int by_begin, int by_count, cudaStream_t s, const char **err) {
+  static_assert(VS == 1 || (VS == 2 && FORM == 2 && BH == 8 && NSUB == 2 && WORDS == 4 && !PW), "pair kernel shape");
   constexpr int SW = 4 * WORDS;
+  constexpr int kW = VS == 2 ? kWarpsV : kWarps;   // warps per CTA
   TiledParams p;
   memset(&p, 0, sizeof p);
   p.W = g.W; p.H = g.H; p.B = g.B; p.R = g.R;
   p.nbx = g.nbx; p.nby = g.nby;
-  p.by_begin = by_begin; p.by_count = by_count;
+  p.by_begin = by_begin; p.by_count = by_count / VS;   // item rows
   p.npairs = npairs;
   p.strips_per_row = (g.nbx + NSUB - 1) / NSUB;
-  p.wh = 2 * g.R + BH;
+  p.wh = 2 * g.R + BH * VS;
   const int static_smem = 2048;  // static shared memory (barriers, counters) + alignment slack
   const int ebytes = (16 - (g.R % 16)) % 16;  // SW is a multiple of 16, so every item has the same phase
   // Choose strips per item (ns) and vertical parts per column with a small cost model:
   // a CTA's time ~ (items it owns) x (chunks per item) x (instructions per task) / warps.
   // ns is bounded by the TMA box (<= 256 B per row) and by two stages of shared memory.
-  const long long rows_total = (long long)by_count * npairs;
+  const long long rows_total = (long long)(by_count / VS) * npairs;
   const int nc = 2 * g.R + 1;
   double best_cost = 1e300;
   int best_ns = 0, best_parts = 1;
@@ -730,8 +1024,8 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   auto stage_size = [&](int ns) {
     const int wb = kWinPitch;
     const int win = ((wb * p.wh) + 127) & ~127;
-    const int stile = FORM == 2 ? ((s_pitch_of(ns) * (2 * g.R + 1) * 4 + 127) & ~127) : 0;
-    return (win + ns * SW * BH + stile + ns * NSUB * 8 + 127) & ~127;
+    const int stile = FORM == 2 ? ((s_pitch_of(ns) * (2 * g.R + 1 + BH * (VS - 1)) * 4 + 127) & ~127) : 0;
+    return (win + ns * SW * BH * VS + stile + ns * NSUB * VS * 8 + 127) & ~127;
   };
   for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
     const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
@@ -752,10 +1046,10 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       // per task: L candidates x BH rows x WORDS cross-term ops (x2 for FORM 0), plus per streamed
       // row the loads, shifts and (FORM 1) the row-energy ops
       const double per_row = FORM == 1 ? (2.0 * WORDS + 8.0) : (2.0 * WORDS + 6.0);
-      const double task = (double)L * BH * WORDS * (FORM >= 1 ? 1.0 : 2.0) + (double)(L + BH - 1) * per_row + 250.0;
+      const double task = (double)L * BH * VS * WORDS * (FORM >= 1 ? 1.0 : 2.0) + (double)(L + BH * VS - 1) * per_row + 250.0;
       // warps flow from one item into the next, so chunks only quantise over the CTA's whole run
       // + per item: every warp's barrier wait / item decode / counter round trips, the re-arm and the publish
-      const double cost = (double)((per_cta * chunks + kWarps - 1) / kWarps) * task + 300.0 * per_cta;
+      const double cost = (double)((per_cta * chunks + kW - 1) / kW) * task + 300.0 * per_cta;
       if (cost < best_cost * 0.999) { best_cost = cost; best_ns = ns; best_parts = parts; }
     }
   }
@@ -770,7 +1064,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.win_bytes = ((p.wb * p.wh) + 127) & ~127;
   p.cur_pitch = ns * SW;
   p.s_pitch = s_pitch_of(ns);
-  p.s_rows = 2 * g.R + 1;
+  p.s_rows = 2 * g.R + 1 + BH * (VS - 1);
   p.s_bytes = (p.s_pitch * p.s_rows * 4 + 127) & ~127;
   p.e_s = e_s;
   p.stage_bytes = stage_size(ns);
@@ -779,7 +1073,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.out = o;
   // peer stores from inside the kernel exist for the two default formulations on full-width
   // frames; other launches leave the peers to the caller's store kernel
-  constexpr bool kPeerVariant = FORM >= 1 && !PW;
+  constexpr bool kPeerVariant = FORM >= 1 && !PW && VS == 1;
   const bool peer = kPeerVariant && plan->npeer > 0;
   p.npeer = peer ? plan->npeer : 0;
   for (int q = 0; q < p.npeer; q++) p.peer[q] = plan->peer[q];
@@ -797,7 +1091,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   const cuuint64_t strides[2] = {(cuuint64_t)f.pitch, (cuuint64_t)(npairs > 1 ? f.pair_stride : f.pitch * g.H)};
   const cuuint32_t estr[3] = {1, 1, 1};
   const cuuint32_t box_ref[3] = {(cuuint32_t)p.wb, (cuuint32_t)p.wh, 1};
-  const cuuint32_t box_cur[3] = {(cuuint32_t)p.cur_pitch, (cuuint32_t)BH, 1};
+  const cuuint32_t box_cur[3] = {(cuuint32_t)p.cur_pitch, (cuuint32_t)(BH * VS), 1};
   CUresult r1 = enc(&map_ref, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)f.ref, dims, strides, box_ref, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -884,19 +1178,25 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   if (getenv("ME_B200_VERBOSE"))
     fprintf(stderr, "[me_b200] tiled<%d,%d,%d,form %d> ns=%d parts=%d items=%d stages=%d stage=%d B smem=%d B s_pitch=%d\n",
             WORDS, BH, NSUB, FORM, p.ns, p.parts_target, p.total_items, p.stages, p.stage_bytes, smem, p.s_pitch);
-  auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, false>;
-  if constexpr (kPeerVariant) {
-    if (peer) kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, true>;
+  const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
+  cudaError_t e;
+  if constexpr (VS == 2) {
+    e = cudaFuncSetAttribute(tiled_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) tiled_pair_kernel<<<grid, kWarpsV * 32, smem, s>>>(map_ref, map_cur, map_s, p);
+  } else {
+    auto kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, false>;
+    if constexpr (kPeerVariant) {
+      if (peer) kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, true>;
+    }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
     *err = "cudaFuncSetAttribute(tiled)";
     if (d_s) cudaFreeAsync(d_s, s);
     cudaFreeAsync(d_ctr, s);
     return e;
   }
-  const int grid = p.total_items < plan->sms ? p.total_items : plan->sms;
-  kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
   plan->kernels_launched++;
   e = cudaGetLastError();
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
@@ -946,7 +1246,33 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   if (t1 > r0) {
     // the energy-table pre-pass (two small launches) only pays off once there is enough work
     const bool table = plan->form == 2 && (long long)npairs * g.W * g.H >= (plan->form_env_forced ? 0 : 2000000LL);
-    if (table) {
+    // 8x8 blocks with the energy table on full-width frames: block rows whose window is not clamped
+    // vertically go through the pair kernel two at a time, the rest through the single-row kernel
+    int pa = t1, pb = t1;   // block rows [pa, pb) run as pairs
+    // Measured (profiles/README.md): +12 % at +-8, +6 % at +-64, +1..2 % at +-12 / +-32 on 4K frames, but -1..-3 %
+    // on 1080p / CIF frames at +-12 -- so: 4K-class frames and the spans where it clearly wins
+    const bool pair_pays = g.H >= 1440 || g.R <= 8 || g.R >= 48;
+    const char *pe = getenv("ME_B200_PAIR");   // 0 / 1 force it off / on (measurements, tests)
+    const bool want_pair = pe ? pe[0] == '1' : pair_pays;
+    if (table && want_pair && g.B == 8 && g.W % 8 == 0 && plan->npeer == 0) {
+      const int first = (g.R + 7) / 8;                        // y0 >= R
+      const int last = (g.H - g.R - 16) / 8;                  // y0 + 16 + R <= H  (upper row of the last pair)
+      pa = r0 > first ? r0 : first;
+      const int top = (t1 - 2 < last ? t1 - 2 : last);        // largest admissible upper row
+      pb = top >= pa ? pa + ((top - pa) / 2 + 1) * 2 : pa;
+      if (pb - pa < 8) pa = pb = t1;                          // not worth a launch of its own
+    }
+    if (table && pb > pa) {
+      if (pa > r0) e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, r0, pa - r0, s, err);
+      if (e == cudaSuccess) {
+        e = launch_shape_pw<4, 8, 2, 2, false, 2>(plan, g, f, npairs, o, pa, pb - pa, s, err);
+        if (e == cudaErrorInvalidConfiguration) {   // the bigger stage does not fit: single rows
+          (void)cudaGetLastError();
+          e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, pa, pb - pa, s, err);
+        }
+      }
+      if (e == cudaSuccess && t1 > pb) e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, pb, t1 - pb, s, err);
+    } else if (table) {
       if (g.B == 16) e = launch_shape<4, 16, 1, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
       else e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
     } else if (plan->form >= 1) {

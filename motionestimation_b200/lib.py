@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "me_b200_search_u8": (C.c_int, [vp, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_submit": (C.c_int, [vp, C.c_int, u8p, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_wait": (C.c_int, [vp, C.c_int]),
+        "me_b200_set_ingest_helper": (C.c_int, [vp, C.c_int, C.c_int]),
         "me_b200_submit_sequence": (C.c_int, [vp, C.c_int, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_search_sequence_u8": (C.c_int, [vp, u8p, C.c_int, i32p, i32p, u32p, f32p]),
         "me_b200_host_alloc": (vp, [C.c_size_t]),
@@ -309,6 +310,11 @@ class Estimator:
 
     def wait(self, slot: int):
         self._check(self._lib.me_b200_wait(self._h, slot), "me_b200_wait")
+
+    def set_ingest_helper(self, helper_device: int, helper_pairs: int):
+        """The last `helper_pairs` pairs of every submit travel over `helper_device`'s host link and NVLink."""
+        self._check(self._lib.me_b200_set_ingest_helper(self._h, helper_device, helper_pairs),
+                    "me_b200_set_ingest_helper")
 
     # -- device-resident path (torch tensors provide the memory) ---------------------------
     def search_device(self, d_cur, d_ref, pitch: int, pair_stride: int, npairs: int,

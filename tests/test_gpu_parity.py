@@ -64,6 +64,10 @@ RANDOM_GEOMS = [
     # 16-column warps (R = 4 / 3), a single block, tall and narrow
     (16, 1, 64, 33), (16, 2, 160, 47), (16, 3, 48, 31), (16, 4, 96, 24), (16, 4, 528, 40), (16, 3, 272, 64),
     (16, 2, 16, 16), (16, 1, 16, 200), (16, 4, 48, 17), (16, 2, 1040, 20), (16, 3, 32, 36), (16, 1, 560, 18),
+    # 8x8 blocks tall enough for the pair kernel (two block rows per item on the rows whose window is not
+    # clamped vertically; with the energy table, i.e. ME_B200_FORM=2 for launches this small): even / odd
+    # numbers of interior rows, a partial bottom row, several vertical parts
+    (8, 12, 352, 288), (8, 5, 200, 160), (8, 32, 256, 200), (8, 7, 120, 144), (8, 16, 136, 177), (8, 12, 64, 136),
 ]
 
 
@@ -135,6 +139,7 @@ def test_small_span_full_size(orc, R):
 @pytest.mark.parametrize("B,R,W,H", RANDOM_GEOMS)
 def test_random_differential_formulations(orc, monkeypatch, B, R, W, H, form):
     monkeypatch.setenv("ME_B200_FORM", form)
+    monkeypatch.setenv("ME_B200_PAIR", "1")   # 8x8 with the table: the pair kernel wherever rows can be paired
     test_random_differential(orc, B, R, W, H, me.ME_KERNEL_AUTO)
 
 
@@ -529,3 +534,44 @@ def test_search_is_cuda_graph_capturable(orc):
     exp = orc.search(me.foreman(4), ref8, B, R)
     assert np.array_equal(mvx.cpu().numpy(), exp["mvx"]) and np.array_equal(mvy.cpu().numpy(), exp["mvy"])
     assert np.array_equal(ssd.cpu().numpy().view(np.uint32), exp["ssd"])
+
+
+def test_ingest_helper_argument_checks():
+    """me_b200_set_ingest_helper: the helper must be another GPU; fewer helper pairs than max_pairs."""
+    with me.Estimator(352, 288, 8, 12, max_pairs=4) as est:
+        with pytest.raises(me.MeError) as ei:
+            est.set_ingest_helper(0, 1)            # the context's own device
+        assert ei.value.code == me.ME_ERR_INVALID_ARG
+        with pytest.raises(me.MeError):
+            est.set_ingest_helper(me.device_count(), 1)
+        est.set_ingest_helper(-1, 0)               # switching it off is always fine
+
+
+@pytest.mark.skipif(me.device_count() < 2, reason="needs two GPUs with peer access")
+def test_ingest_helper_routes_pairs_over_a_peer_gpu(orc):
+    """Part of every submit travels host -> GPU 1 -> (NVLink peer copy) -> GPU 0; results are unchanged."""
+    lib = me.load_library()
+    W, H, B, R, P = 352, 288, 8, 12, 6
+    frames = [me.foreman(2), me.foreman(4), me.shifted_noise_pair(W, H, seed=1)[0], me.random_pair(W, H, 2)[0],
+              me.foreman(1), me.shifted_noise_pair(W, H, seed=2)[0]]
+    cur = np.stack(frames)
+    ref = np.stack([me.foreman(1)] * P)
+    n, nb = W * H, (W // B) * (H // B)
+    with me.Estimator(W, H, B, R, device=0, max_pairs=P) as est:
+        plain = est.search_u8(cur, ref)
+        est.set_ingest_helper(1, 2)
+        for hp in (2, 5):
+            est.set_ingest_helper(1, hp)
+            bufs = [lib.me_b200_host_alloc(sz) for sz in (P * n, P * n, 4 * P * nb, 4 * P * nb, 4 * P * nb)]
+            C.memmove(bufs[0], cur.ctypes.data, P * n)
+            C.memmove(bufs[1], ref.ctypes.data, P * n)
+            for rep in range(3):
+                est.submit_ptr(rep % 4, bufs[0], bufs[1], P, bufs[2], bufs[3], bufs[4], 0)
+                est.wait(rep % 4)
+                for k, name in ((2, "mvx"), (3, "mvy"), (4, "ssd")):
+                    got = np.ctypeslib.as_array((C.c_int32 * (P * nb)).from_address(bufs[k])).reshape(P, nb)
+                    assert np.array_equal(got.view(np.uint32), plain[name].view(np.uint32)), (hp, rep, name)
+            for b_ in bufs:
+                lib.me_b200_host_free(b_)
+    o = orc.search(cur[1], ref[1], B, R)
+    assert np.array_equal(plain["mvx"][1], o["mvx"])
