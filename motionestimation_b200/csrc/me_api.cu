@@ -50,6 +50,11 @@ struct me_b200_ctx {
   unsigned long long *d_evals = nullptr;  // fast search: candidate evaluations so far
   int *d_peer_status = nullptr;           // peer barrier: 1 after a time-out
   cudaEvent_t band_events[32] = {nullptr}; // drop-in call: "band c has been uploaded" (created on first use)
+  // drop-in call, arriving-frame mode: device flag "rows resident" + give-up status, the pinned values the
+  // copy stream writes into the flag, and the call counter that keeps flag values of different calls apart
+  unsigned int *d_arrive = nullptr;        // [0] flag, [1] status
+  unsigned int *h_arrive = nullptr;        // pinned, one value per band
+  unsigned int arrive_epoch = 0;
   char err[256] = {0};
   // scratch for the int-frame drop-in path
   uint8_t *h_cur = nullptr, *h_ref = nullptr;  // pinned, W*H each
@@ -397,6 +402,8 @@ void me_b200_destroy(me_b200_ctx *ctx) {
     if (ctx->plan) me::tiled_plan_destroy(ctx->plan);
     cudaFree(ctx->d_evals);
     cudaFree(ctx->d_peer_status);
+    cudaFree(ctx->d_arrive);
+    cudaFreeHost(ctx->h_arrive);
     for (int i = 0; i < 32; i++)
       if (ctx->band_events[i]) cudaEventDestroy(ctx->band_events[i]);
     cudaFreeHost(ctx->h_cur);
@@ -1070,13 +1077,24 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   double t_band[kMaxChunks + 1] = {0}, t_launch[kMaxChunks + 1] = {0};
   PackPool *pool = pack_pool();
   if (!pool) return ME_ERR_NOMEM;
+  // One launch for the whole frame while it is still arriving (tiled_plan_set_arrive) when the geometry
+  // allows it -- then the bands are only the granularity of the arrival flag; otherwise one launch per band.
+  bool arrive = n >= (1u << 20) && cost == ME_COST_MSE && search == ME_SEARCH_FULL && ctx->kernel == ME_KERNEL_TILED &&
+                ctx->plan && me::tiled_arrive_supported(ctx->g);
+  if (const char *e = getenv("ME_B200_DROPIN_ARRIVE")) arrive = arrive && e[0] != '0';
   int nbands = n >= (1u << 20) ? 4 : 1;
   if (const char *e = getenv("ME_B200_DROPIN_BANDS")) nbands = atoi(e);
   if (nbands < 1) nbands = 1;
   if (nbands > kMaxChunks) nbands = kMaxChunks;
   if (nbands > nby) nbands = nby;
+  if (nbands < 2) arrive = false;
   if (!ctx->band_events[0]) {
     for (int i = 0; i < kMaxChunks; i++) ME_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_events[i], cudaEventDisableTiming));
+  }
+  if (arrive && !ctx->d_arrive) {
+    ME_CUDA(ctx, cudaMalloc((void **)&ctx->d_arrive, 256));
+    ME_CUDA(ctx, cudaMemset(ctx->d_arrive, 0, 256));
+    ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_arrive, sizeof(unsigned int) * (kMaxChunks + 1), cudaHostAllocDefault));
   }
   PackJob job;
   job.src[0] = refFrame; job.src[1] = pf->frame;
@@ -1105,6 +1123,12 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   rc = ME_OK;
   me::Frames fr{sl.d_cur, sl.d_ref, ctx->pitch, ctx->frame_bytes};
   me::Out out{sl.d_mvx, sl.d_mvy, sl.d_ssd, sl.d_score};
+  unsigned int arrive_base = 0;
+  if (arrive) {
+    ctx->arrive_epoch = (ctx->arrive_epoch + 1) & 0x7fffu;
+    arrive_base = ctx->arrive_epoch << 16;
+    for (int c = 0; c < nbands; c++) ctx->h_arrive[c] = arrive_base + (unsigned int)job.row0[1][c + 1];
+  }
   for (int c = 0; c < nbands && ce == cudaSuccess && rc == ME_OK; c++) {
     for (int f = 0; f < 2 && ce == cudaSuccess; f++) {
       pool->wait_chunk(2 * c + f);
@@ -1118,6 +1142,21 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
         ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, copy_stream);
     }
     if (trace) t_band[c] = getTimeStamp();
+    if (arrive) {
+      // rows of band c (and the reference rows R below) are resident once this 4-byte copy has run
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(ctx->d_arrive, ctx->h_arrive + c, sizeof(unsigned int), cudaMemcpyHostToDevice, copy_stream);
+      if (c == 0 && ce == cudaSuccess) {
+        ce = cudaEventRecord(ctx->band_events[0], copy_stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sl.stream, ctx->band_events[0], 0);
+        if (ce == cudaSuccess && !(pool->bad_bits() & ~0xffu)) {
+          me::tiled_plan_set_arrive(ctx->plan, ctx->d_arrive, arrive_base, (int *)(ctx->d_arrive + 1));
+          rc = run_search(ctx, fr, 1, 0, nby, out, sl.stream);
+        }
+      }
+      if (trace) t_launch[c] = getTimeStamp();
+      continue;
+    }
     if (ce == cudaSuccess) ce = cudaEventRecord(ctx->band_events[c], copy_stream);
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sl.stream, ctx->band_events[c], 0);
     if (ce == cudaSuccess && (pool->bad_bits() & ~0xffu)) break;   // a pixel outside 0..255: no point in searching
@@ -1137,8 +1176,16 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(ctx->h_mvy, sl.d_mvy, ob, cudaMemcpyDeviceToHost, sl.stream);
     if (ce == cudaSuccess && ssd) ce = cudaMemcpyAsync(ctx->h_ssd, sl.d_ssd, ob, cudaMemcpyDeviceToHost, sl.stream);
     if (ce == cudaSuccess && scores) ce = cudaMemcpyAsync(ctx->h_score, sl.d_score, ob, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess && arrive)   // the give-up status of the arriving-frame launch travels with the field
+      ce = cudaMemcpyAsync(ctx->h_arrive + kMaxChunks, ctx->d_arrive + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                           sl.stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(sl.stream);
     if (ce != cudaSuccess) rc = fail_cuda(ctx, ce, "download (device to host)");
+    if (rc == ME_OK && arrive && ctx->h_arrive[kMaxChunks]) {
+      cudaMemset(ctx->d_arrive + 1, 0, sizeof(unsigned int));
+      snprintf(ctx->err, 256, "the frame upload did not arrive while the search was waiting for it");
+      rc = ME_ERR_CUDA;
+    }
   }
   if (rc != ME_OK) {
     cudaStreamSynchronize(copy_stream);

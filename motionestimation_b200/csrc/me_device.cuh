@@ -59,6 +59,12 @@ int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers);
 void tiled_plan_fused_rows(const TiledPlan *plan, int *begin, int *end);
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err_text);
+// "Arriving frame": the next launch_tiled (whole frame, one pair) may start while the pair is still being
+// uploaded top to bottom.  *flag (device memory) = base + number of current-frame rows resident, with the
+// reference rows R below them; the uploader advances it in stream order after each piece.  Items wait for
+// their rows; *status becomes 1 if one gave up after ~1 s.  (nullptr switches it off.)
+bool tiled_arrive_supported(const Geom &g);
+void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status);
 
 // SSIM-cost full search (me_ssim.cu; reference: src/cpu/main_ssim.c + src/common/ssim.c).
 // Out.score = best SSIM, Out.ssd = 1 when some candidate scored above 0 (else MV = (0,0)).

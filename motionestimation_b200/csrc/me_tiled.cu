@@ -116,6 +116,12 @@ struct TiledParams {
   // peer GPUs (peer-mapped memory), so no collective follows the search
   int npeer;
   Out peer[kMaxPeerOuts];
+  // "arriving frame" launches (the drop-in call): the frame pair is still being uploaded, top to bottom, while
+  // the kernel runs.  *arrive_flag = arrive_base + number of current-frame rows that are resident (and the
+  // reference rows R below them); an item waits for its rows before it starts its TMA loads.
+  const unsigned int *arrive_flag;
+  unsigned int arrive_base;
+  int *arrive_status;   // set to 1 when an item gave up waiting
 };
 
 // ---------------------------------------------------------------- item geometry
@@ -158,7 +164,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int WORDS, int BH, int NSUB, int FORM, bool PW, bool PEER>
+template <int WORDS, int BH, int NSUB, int FORM, bool PW, bool PEER, bool ARRIVE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur,
                     const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_sh,
@@ -205,6 +211,23 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       left_ctr[stage] = 0;
       item_id[stage] = it;
       item_s[stage] = I;
+    }
+    if constexpr (ARRIVE) {
+      // the frame is still arriving: wait until the rows of this item are resident (the uploads and the
+      // flag updates are ordered on one copy stream; items are handed out top to bottom)
+      if (lane == 0) {
+        const unsigned need = p.arrive_base + (unsigned)min(p.H, I.y0 + BH);
+        for (int spins = 0;; spins++) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.arrive_flag) : "memory");
+          if ((int)(v - need) >= 0) break;
+          if (spins > (1 << 22)) {   // ~ 1 s: the upload failed or stalled; the host reports it
+            *p.arrive_status = 1;
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) {
@@ -918,6 +941,10 @@ struct TiledPlan {
   // before that, so another kernel may serve the same request)
   bool outputs_enqueued = false;
   char err[160] = {0};
+  // "arriving frame" mode of the NEXT launch (tiled_plan_set_arrive); consumed by that launch
+  const unsigned int *arrive_flag = nullptr;
+  unsigned int arrive_base = 0;
+  int *arrive_status = nullptr;
 };
 
 static int env_form() {
@@ -982,6 +1009,21 @@ int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers) {
   plan->fused_begin = plan->fused_end = 0;
   plan->fused_launch = false;
   return 0;
+}
+
+void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status) {
+  if (!plan) return;
+  plan->arrive_flag = flag;
+  plan->arrive_base = base;
+  plan->arrive_status = status;
+}
+
+bool tiled_arrive_supported(const Geom &g) {
+  // every block row must run on the tuned kernel (a generic tail launch would need the whole frame), and
+  // the on-the-fly energy formulation is the one without a pre-pass over the whole reference frame
+  if (!shape_ok(g.B) || env_form() == 0 || g.H >= 65536) return false;
+  const int hrem = g.H % g.B;
+  return hrem == 0 || hrem == g.B / 2;
 }
 
 void tiled_plan_fused_rows(const TiledPlan *plan, int *begin, int *end) {
@@ -1188,6 +1230,14 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     if constexpr (kPeerVariant) {
       if (peer) kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, true>;
     }
+    if constexpr (FORM == 1) {
+      if (plan->arrive_flag && !peer) {
+        p.arrive_flag = plan->arrive_flag;
+        p.arrive_base = plan->arrive_base;
+        p.arrive_status = plan->arrive_status;
+        kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, false, true>;
+      }
+    }
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) kern<<<grid, kThreads, smem, s>>>(map_ref, map_cur, map_s, map_sh, p);
   }
@@ -1237,6 +1287,10 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   // any other partial bottom row is a different block shape and runs on the generic kernel
   // as a one-row band.
   plan->outputs_enqueued = false;
+  struct ArriveReset {   // the arriving-frame settings apply to this launch only
+    TiledPlan *p;
+    ~ArriveReset() { p->arrive_flag = nullptr; p->arrive_status = nullptr; }
+  } arrive_reset{plan};
   const int full_rows = g.H / g.B;
   const int hrem = g.H % g.B;
   const int tiled_rows = full_rows + ((plan->form >= 1 && hrem == g.B / 2) ? 1 : 0);
@@ -1245,7 +1299,8 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
     // the energy-table pre-pass (two small launches) only pays off once there is enough work
-    const bool table = plan->form == 2 && (long long)npairs * g.W * g.H >= (plan->form_env_forced ? 0 : 2000000LL);
+    const bool table = plan->form == 2 && !plan->arrive_flag &&
+                       (long long)npairs * g.W * g.H >= (plan->form_env_forced ? 0 : 2000000LL);
     // 8x8 blocks with the energy table on full-width frames: block rows whose window is not clamped
     // vertically go through the pair kernel two at a time, the rest through the single-row kernel
     int pa = t1, pb = t1;   // block rows [pa, pb) run as pairs

@@ -183,6 +183,34 @@ def test_drop_in_prediction_frame(orc):
     assert ei.value.code == me.ME_ERR_UNSUPPORTED
 
 
+@pytest.mark.parametrize("mode", ["arrive", "bands", "one"])
+@pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 32), (1930, 1080, 16, 12), (1920, 1080, 8, 12), (1280, 1000, 16, 20),
+                                     (3840, 2160, 8, 12)])
+def test_drop_in_large_frames_pipelined(orc, monkeypatch, W, H, B, R, mode):
+    """me_b200_search on frames large enough for the pipelined ingest: the int frames are narrowed by the
+    worker threads and uploaded band by band while the search already runs -- as ONE launch whose items wait
+    for their rows ("arrive": the tuned kernel with the on-the-fly energies; needs every block row on that
+    kernel, so 1280x1000 with its odd bottom row runs banded instead), as one launch per band ("bands") or
+    after the whole upload ("one").  Every block against the oracle, twice per mode (the arrival flag is
+    reused across calls), scores and SSDs included."""
+    monkeypatch.setenv("ME_B200_DROPIN_ARRIVE", "1" if mode == "arrive" else "0")
+    if mode == "one":
+        monkeypatch.setenv("ME_B200_DROPIN_BANDS", "1")
+    me.load_library().me_b200_release_cached()
+    pairs = [me.tiled_frames(W, H, 2, 1), me.shifted_noise_pair(W, H, seed=77, shift=(-4, 3))]
+    for c8, r8 in pairs:
+        cur, ref = c8.astype(np.int32).ravel(), r8.astype(np.int32).ravel()
+        pf = me.create_prediction_frame(cur, W, H, B)
+        sc, sd = me.search_prediction_frame(pf, ref, R, want_scores=True)
+        o = orc.search(c8, r8, B, R, nthreads=os.cpu_count())
+        mvx = np.array([pf.blks[i].motion_vectorX for i in range(pf.num_blks)])
+        mvy = np.array([pf.blks[i].motion_vectorY for i in range(pf.num_blks)])
+        assert np.array_equal(mvx, o["mvx"]) and np.array_equal(mvy, o["mvy"])
+        assert np.array_equal(sd, o["ssd"]) and np.array_equal(sc.view(np.uint32), o["score"].view(np.uint32))
+        assert all(pf.blks[i].is_best_match_found == 1 for i in range(0, pf.num_blks, 97))
+    me.load_library().me_b200_release_cached()
+
+
 @pytest.mark.parametrize("args,name", [((), "foreman_yf4_yf1_8_12"), (("4", "15"), "foreman_yf4_yf1_4_15"),
                                        (("4", "7"), "foreman_yf4_yf1_4_7")])
 def test_cli_is_byte_identical(tmp_path, args, name):
