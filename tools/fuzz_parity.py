@@ -1,6 +1,8 @@
 """Randomised parity fuzz on the GPU: random geometries / spans / frame contents, AUTO kernel (and the
 forced formulations) against the oracle.
-usage: python tools/fuzz_parity.py [n_cases] [seed] [mode: mse | ssim | fast | all]"""
+usage: python tools/fuzz_parity.py [n_cases] [seed] [mode: mse | ssim | fast | all | stream | pair]
+(stream: the small-span streaming kernel -- 16x16 blocks, widths that are multiples of 16, spans 1..4, any
+height; pair: 8x8 blocks with the energy table and the two-rows-per-item kernel forced)"""
 import os
 import sys
 
@@ -30,7 +32,16 @@ def main():
         if rng.random() < 0.3:
             H = (H // B) * B + (B // 2 if rng.random() < 0.5 else 0)
         H = max(H, B)
-        mode = mode_arg if mode_arg != "all" else str(rng.choice(["mse", "ssim", "fast"]))
+        if mode_arg == "stream":
+            B, R = 16, int(rng.integers(1, 5))
+            W = 16 * int(rng.integers(1, 70))
+            H = int(rng.integers(16, 300))
+        if mode_arg == "pair":
+            B, R = 8, int(rng.choice([1, 3, 5, 8, 12, 13, 16, 24, 32, 40]))
+            W = 8 * int(rng.integers(2, 60))
+            H = int(rng.integers(8 * (2 * ((R + 7) // 8) + 10), 8 * (2 * ((R + 7) // 8) + 40)))
+        mode = mode_arg if mode_arg not in ("all", "stream", "pair") else (
+            "mse" if mode_arg != "all" else str(rng.choice(["mse", "ssim", "fast"])))
         kind = int(rng.integers(0, 6 if mode == "ssim" else 5))
         if kind == 0:
             cur, ref = me.random_pair(W, H, int(rng.integers(1 << 30)))
@@ -46,6 +57,9 @@ def main():
         else:
             cur, ref = me.inverted_pair(W, H, seed=int(rng.integers(1 << 30)), period=float(rng.uniform(5, 40)))
         form = str(rng.choice(["", "", "2", "1", "0"]))
+        if mode_arg == "pair":
+            form = "2"
+            os.environ["ME_B200_PAIR"] = "1"
         if form:
             os.environ["ME_B200_FORM"] = form
         else:
