@@ -577,11 +577,18 @@ def main():
             if donors:
                 d = max(donors, key=lambda d: spare[d])
                 helpers[r] = (d, hp)
+        helper_error = None
         if rank in helpers:
-            est.set_ingest_helper(helpers[rank][0], helpers[rank][1])     # (local rank == device index on one node)
+            try:   # (local rank == device index on one node; needs every GPU visible to every rank + peer access)
+                if torch.cuda.device_count() <= helpers[rank][0]:
+                    raise RuntimeError("GPU %d is not visible to rank %d" % (helpers[rank][0], rank))
+                est.set_ingest_helper(helpers[rank][0], helpers[rank][1])
+            except Exception as ex:   # the direct path still works, only slower
+                helper_error = repr(ex)
         ingest = {"h2d_gbs_all_ranks_copying": [round(b, 1) for b in bw], "kernel_needs_gbs": round(nd[0], 1),
                   "helpers": {str(r): {"via_gpu": h[0], "pairs_per_submit": h[1], "of": slot_pairs}
                               for r, h in helpers.items()},
+                  "rank0_helper_error": helper_error,
                   "api": "me_b200_set_ingest_helper: host -> helper GPU (its PCIe link) -> NVLink peer copy"}
         sync_all()
 
