@@ -50,10 +50,10 @@ WORKLOADS = {
     # only candidate is the co-located block, one streaming pass over both frames
     "1080p_16x16_pm0": (1920, 1080, 16, 0, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-0"),
     "4k_16x16_pm0": (3840, 2160, 16, 0, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-0"),
-    "1080p_16x16_pm1": (1920, 1080, 16, 1, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-1"),
-    "1080p_16x16_pm2": (1920, 1080, 16, 2, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-2"),
-    "1080p_16x16_pm4": (1920, 1080, 16, 4, 64, "small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-4"),
-    "4k_16x16_pm2": (3840, 2160, 16, 2, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-2"),
+    "1080p_16x16_pm1": (1920, 1080, 16, 1, 256, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-1"),
+    "1080p_16x16_pm2": (1920, 1080, 16, 2, 256, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-2"),
+    "1080p_16x16_pm4": (1920, 1080, 16, 4, 256, "small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-4"),
+    "4k_16x16_pm2": (3840, 2160, 16, 2, 64, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-2"),
     # SSIM-cost full search (src/cpu/main_ssim.c); the first one is that program's default geometry
     "ssim_4k_16x16_pm7": (3840, 2160, 16, 7, 8, "reference SSIM program defaults (main_ssim.c:41-44): synthetic 3840x2160 luma, blk 16, span 7"),
     "ssim_1080p_16x16_pm32": (1920, 1080, 16, 32, 16, "SSIM-cost full search, synthetic 1920x1080 luma, 16x16 blocks, +-32"),

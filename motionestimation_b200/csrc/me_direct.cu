@@ -593,18 +593,20 @@ cudaError_t launch_stream(const Geom &g, const Frames &f, int npairs, const Out 
   }
   StreamParams sp;
   sp.ncg = (g.nbx + CPW - 1) / CPW;
-  // Stripes per pair: every warp runs one stripe, and a launch should be a whole number of "waves" of
-  // the warps the machine holds at once -- with as few stripes as that allows, because every stripe
-  // re-reads 2R rows and fills its ring once.  Stripes are cut evenly (block rows i*n/k), so all
-  // warps of a launch finish together.
+  // Stripes per pair.  Every warp runs one stripe; stripes are cut evenly (block rows i*n/k).  Fewer stripes
+  // re-read fewer rows (2R per stripe) and fill fewer rings, but the warps of a wave finish staggered (the
+  // scheduler favours the oldest warp, and one or two warps cannot fill the FMA-heavy pipe), which costs about
+  // a third of a stripe's time at the end of the launch -- so several short waves, in which finished CTAs are
+  // replaced at once, beat one tall wave (measured, 256 pairs of 1080p +-2: 2 stripes 541 k, 9 stripes 628 k
+  // frames/s; 64 pairs: 9 stripes 509 k, 17 stripes 515 k).
   const long long resident = (long long)sms * MINB * kStreamWarps;
-  long long best_cost = -1;
+  double best_cost = -1.0;
   int best_n = 1;
   for (int n = 1; n <= g.by_count; n++) {
     const int rows = (g.by_count + n - 1) / n;   // block rows of the tallest stripe
     const long long total = (long long)npairs * n * sp.ncg;
     const long long waves = (total + resident - 1) / resident;
-    const long long cost = waves * (rows * 16 + 2 * R + 12);
+    const double cost = ((double)waves + 0.35) * (double)(rows * 16 + 2 * R + 12);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_n = n; }
   }
   if (const char *e = getenv("ME_B200_STREAM_STRIPES")) {
