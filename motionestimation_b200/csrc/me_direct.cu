@@ -2,18 +2,20 @@
 // block), the memory-bound end of the path (only +-0..+-2 ranges are
 // bandwidth-bound with u8 frames).
 //
-// Reference being replaced: the same main.c:18-82 scan as the tuned kernel; with so few
-// candidates the rotating-accumulator streaming of me_tiled.cu cannot amortise its set-up, so
-// this kernel maps B lanes to one (block, candidate) pair instead:
-//   * a CTA owns a 128 x 32 pixel tile of blocks (8 x 2 blocks of 16x16 or 16 x 4 blocks of 8x8);
-//     the current tile and the reference tile + R halo are staged in shared memory once with
-//     coalesced 16-byte loads (each frame byte is read from HBM ~1.1 times);
-//   * a group of B lanes scores one (block, candidate) unit, one block row per lane: the aligned
-//     reference words around the candidate column are funnel-shifted into place and compared with
-//     VABSDIFF4.U8 + IDP.4A.U8.U8 (exact integer SSD), the rows are added with shuffles;
-//   * key = ssd << 8 | raster index of the candidate in the (2R+1)^2 grid, one 32-bit shared
-//     atomicMin per candidate; the unsigned minimum is the reference's first strict minimum in
-//     y-major/x-minor order (main.c:53-62) because clamped-away candidates are simply skipped.
+// Reference being replaced: the same main.c:18-82 scan as the tuned kernel.  With so few candidates
+// the rotating-accumulator streaming of me_tiled.cu cannot amortise its per-task set-up, so three
+// dedicated kernels run here (launch_direct picks):
+//   * zero_span_kernel          R = 0: one streaming pass over both frames from global memory;
+//   * stream_search_kernel      1 <= R <= 4, 16x16 blocks, width a multiple of 16: a warp walks down a
+//                               stripe of the frame, rows arrive by TMA, every (dx, dy) of a block column is
+//                               a live accumulator in registers -- no per-candidate set-up at all;
+//   * direct_search_kernel      everything else (8x8 blocks, other widths): a CTA stages a 128 x 32 pixel
+//                               tile + halo in shared memory, a group of B lanes (or one thread) scores one
+//                               (block, candidate) with VABSDIFF4.U8 + IDP.4A.U8.U8, 32-bit shared atomicMin
+//                               of ssd << 8 | raster index.
+// In all of them the unsigned minimum of (cost, raster index of the candidate) is the reference's first
+// strict minimum in y-major/x-minor order (main.c:53-62), and clamped-away candidates (main.c:73-76) are
+// simply never folded in.
 #include <stdlib.h>
 
 #include "me_device.cuh"

@@ -87,6 +87,12 @@ constexpr int kMaxPeerOuts = 7;  // other GPUs of one NVSwitch domain
 // sum cur^2 at all; the publishing lane adds it back once per block.  2*dot <= 2*64*255^2 <
 // kBias8 = 2^23 keeps t >= 0, and t <= 64*255^2 + 2^23 < 2^24 keeps it inside the 24-bit key field.
 constexpr uint32_t kBias8 = 1u << 23;
+// FORM 3 (16x16 blocks, 256 pixels): the same idea.  t = (E + kBias16) - 2*dot lies in (0, 2^25), so the
+// per-thread key is t << 7 | dy relative to the first candidate row of the thread's vertical part (parts are
+// limited to 113 candidates), and the shared 64-bit key is t << 24 | dy << 16 | dx.  No task computes
+// sum cur^2 (64 IDP.4A per task on the saturated pipe, measured worth 1.7 %); the publishing lane adds it.
+constexpr uint32_t kBias16 = 1u << 24;
+constexpr int kMaxM16 = 7;   // FORM 3: part length m*16 + 1 <= 113 < 128
 
 struct TiledParams {
   int W, H, B, R;
@@ -135,7 +141,7 @@ struct __align__(16) Item {
   int pad_[2];               // 16 ints: four 16-byte shared-memory loads
 };
 
-template <int BH>
+template <int BH, int MAXM = 1 << 20>
 __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
   Item I;
   const int per_pair = p.items_per_row * p.by_count;
@@ -153,7 +159,7 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
   const int dy_hi = min(2 * p.R, p.H - I.h - I.y0 + p.R);
   I.nc = dy_hi - I.dy_lo + 1;
   const int want = (I.nc + p.parts_target - 1) / p.parts_target;
-  I.m = min((want - 1 + BH - 1) / BH, (I.nc - 1) / BH);
+  I.m = min(min((want - 1 + BH - 1) / BH, (I.nc - 1) / BH), MAXM);
   const int L = I.m * BH + 1;
   I.nparts = (I.nc + L - 1) / L;
   I.tpp = I.ns * (2 * p.R + 1);
@@ -183,7 +189,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   const int lane = threadIdx.x & 31;
   const int cur_off = p.win_bytes;                       // byte offsets inside a stage
   const int s_off = p.win_bytes + p.cur_pitch * BH;      // FORM 2: energy tile
-  const int best_off = s_off + (FORM == 2 ? p.s_bytes : 0);
+  const int best_off = s_off + (FORM >= 2 ? p.s_bytes : 0);
+  static_assert(FORM != 3 || (BH == 16 && NSUB == 1 && !PW && !PEER), "FORM 3 is the 16x16 table formulation");
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
   // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
@@ -204,7 +211,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       __syncwarp();
       return;
     }
-    const Item I = decode_item<BH>(p, it);
+    const Item I = decode_item<BH, (FORM == 3 ? kMaxM16 : (1 << 20))>(p, it);
     for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
     if (lane == 0) {
       chunk_ctr[stage] = 0;
@@ -234,12 +241,12 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // order the generic-proxy accesses to this stage before the async-proxy (TMA) writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
-      if (FORM == 2) bytes += (uint32_t)(p.s_pitch * p.s_rows * 4);
+      if (FORM >= 2) bytes += (uint32_t)(p.s_pitch * p.s_rows * 4);
       mbar_arrive_expect_tx(&full_bar[stage], bytes);
       // 16-byte aligned origin: e bytes left of the window origin x0 - R
       tma_load_3d(sb, &map_ref, &full_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
       tma_load_3d(sb + cur_off, &map_cur, &full_bar[stage], I.strip0 * SW, I.y0, I.pair);
-      if (FORM == 2) {
+      if (FORM >= 2) {
         // energy tile: rows = window-relative dy 0..2R.  The half-height bottom row has its own
         // table whose row 0 is dy = 0 of that block row.
         if (I.h == BH)
@@ -331,21 +338,25 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       constexpr int pitchw = kWinPitch >> 2;
       const int x_strip = (I.strip0 + st) * SW;
       // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
-      int dy_fin = I.dy_lo + c0 - (BH - 1);
+      // (FORM 3: relative to the part's first candidate row dy_base, so that it fits 7 bits)
+      const int dy_base = I.dy_lo + c0;
+      int dy_fin = (FORM == 3 ? 0 : dy_base) - (BH - 1);
 
       // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
       uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
       const bool half = I.h != BH;          // bottom block row of height BH/2
       constexpr bool kBiased = FORM == 2 && BH == 8;   // see kBias8
-      if (FORM >= 1 && !kBiased) {
+      if (FORM >= 1 && FORM != 3 && !kBiased) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
           uint32_t a4[4] = {0u, 0u, 0u, 0u};  // four independent IDP chains instead of one long one
+#ifndef ME_EXPERIMENT_NOCURSQ   // (experiment only, wrong results: what would dropping sum cur^2 from the tasks be worth?)
 #pragma unroll
           for (int r = 0; r < BH; r++)
 #pragma unroll
             for (int w = 0; w < WPB; w++)
               a4[(r * WPB + w) & 3] = __dp4a(cur[r][b * WPB + w], cur[r][b * WPB + w], a4[(r * WPB + w) & 3]);
+#endif
           srun[b] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
 #pragma unroll
           for (int r = 0; r < BH; r++) qh[b][r] = 0u;
@@ -438,14 +449,16 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
                 // candidate complete: fold (ssd << 8 | dy) into the running minimum
                 uint32_t ssd = a;
                 if (FORM == 1) ssd = srun[b] - 2u * a;
-                if (FORM == 2) {
+                if (FORM >= 2) {
                   // (A + E) - a - a: one IADD3 on the ALU pipe instead of an IMAD on the saturated FMA pipe
-                  // (8x8: the table entry already holds E + kBias8 and A is added back at publish time)
-                  const uint32_t ae = kBiased ? spf[b * BW] : srun[b] + spf[b * BW];
+                  // (8x8 and FORM 3: the table entry already holds E + bias and A is added back at publish time)
+                  const uint32_t ae = (kBiased || FORM == 3) ? spf[b * BW] : srun[b] + spf[b * BW];
                   asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %2; }" : "=r"(ssd) : "r"(ae), "r"(a));
                 }
                 uint32_t key;
-                if constexpr (BH == 8) {
+                if constexpr (FORM == 3) {
+                  key = (ssd << 7) + (uint32_t)(dy_fin + s_);   // t << 7 | part-relative dy
+                } else if constexpr (BH == 8) {
                   // ssd < 2^24 and dy < 2^8: a byte permute builds ssd << 8 | dy on the ALU pipe.  Left
                   // to itself ptxas emits IMAD(ssd, 0x100, dy) here -- on the FMA-heavy pipe the
                   // IDP.4A stream already saturates, where 8x8 blocks finish a candidate every 16 IDP
@@ -476,13 +489,14 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           }
           group(s_);
 #endif
-          if (FORM == 2) spf += s_pitch;  // next step finishes the candidate one row further down
+          if (FORM >= 2) spf += s_pitch;  // next step finishes the candidate one row further down
         }
         dy_fin += BH;
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
-      const unsigned peers = __match_any_sync(0xffffffffu, active ? st : -1 - lane);
+      // (FORM 3: the keys of one group must share dy_base, i.e. the vertical part as well as the strip)
+      const unsigned peers = __match_any_sync(0xffffffffu, active ? (FORM == 3 ? row : st) : -1 - lane);
       const bool leader = (peers & (0u - peers)) == (1u << lane);
 #pragma unroll
       for (int b = 0; b < NSUB; b++) {
@@ -493,8 +507,13 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         const uint32_t key = ok ? bestk[b] : kNoKey;
         const uint32_t mkey = __reduce_min_sync(peers, key);
         const uint32_t mdx = __reduce_min_sync(peers, key == mkey ? (uint32_t)dx : 0xffffu);
-        if (leader && mkey != kNoKey)
-          atomicMin(&best[st * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
+        if (leader && mkey != kNoKey) {
+          if constexpr (FORM == 3)   // t << 24 | absolute dy << 16 | dx  (t has 25 bits, dy 8, dx 8)
+            atomicMin(&best[st * NSUB + b], ((unsigned long long)(mkey >> 7) << 24) |
+                                                ((unsigned long long)((mkey & 127u) + (uint32_t)dy_base) << 16) | mdx);
+          else
+            atomicMin(&best[st * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
+        }
       }
     }
     // ---- leave the item; the last warp out publishes it and re-arms the stage
@@ -511,8 +530,24 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         const int bx = I.strip0 * NSUB + b;
         if (bx < p.nbx) {
           const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[b]);
-          const uint32_t k32 = (uint32_t)(key >> 32);
-          uint32_t ssd = k32 >> 8;
+          // key layouts: ssd << 40 | dy << 32 | dx;  FORM 3: t << 24 | dy << 16 | dx (t << 8 | dy would need 33 bits)
+          const uint32_t k32 = FORM == 3 ? (uint32_t)(key >> 16) : (uint32_t)(key >> 32);   // low byte: dy
+          const uint32_t kdx = FORM == 3 ? (uint32_t)key & 0xffffu : (uint32_t)key;
+          uint32_t ssd = FORM == 3 ? (uint32_t)(key >> 24) : k32 >> 8;
+          if constexpr (FORM == 3) {
+            // un-bias: ssd = t - kBias16 + sum cur^2 of this block, from the stage's current tile (the rows
+            // below a half-height block are zero-filled by the TMA load)
+            const uint32_t *ct = reinterpret_cast<const uint32_t *>(sb + cur_off) + b * (BW / 4);
+            uint32_t a2[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int r = 0; r < BH; r++)
+#pragma unroll
+              for (int w = 0; w < BW / 4; w++) {
+                const uint32_t v = ct[r * (p.cur_pitch >> 2) + w];
+                a2[w & 3] = __dp4a(v, v, a2[w & 3]);
+              }
+            ssd = ssd - kBias16 + ((a2[0] + a2[1]) + (a2[2] + a2[3]));
+          }
           if constexpr (FORM == 2 && BH == 8) {
             // un-bias: ssd = t - kBias8 + sum cur^2 of this block, from the stage's current tile (rows
             // below a half-height block are zero-filled by the TMA load)
@@ -528,7 +563,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
             ssd = ssd - kBias8 + a2;
           }
           const size_t oi = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
-          if (p.out.mvx) p.out.mvx[oi] = (int)(uint32_t)key - p.R;   // main.c:58
+          if (p.out.mvx) p.out.mvx[oi] = (int)kdx - p.R;             // main.c:58
           if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
           if (p.out.ssd) p.out.ssd[oi] = ssd;
           const int bw = min(BW, p.W - bx * BW);
@@ -539,7 +574,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
             // plain kernel's code is untouched -- its placement is worth more than 1 %)
             for (int q = 0; q < p.npeer; q++) {
               const Out &po = p.peer[q];
-              if (po.mvx) po.mvx[oi] = (int)(uint32_t)key - p.R;
+              if (po.mvx) po.mvx[oi] = (int)kdx - p.R;
               if (po.mvy) po.mvy[oi] = (int)(k32 & 0xff) - p.R;
               if (po.ssd) po.ssd[oi] = ssd;
               if (po.score) po.score[oi] = score;
@@ -1066,13 +1101,13 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   auto stage_size = [&](int ns) {
     const int wb = kWinPitch;
     const int win = ((wb * p.wh) + 127) & ~127;
-    const int stile = FORM == 2 ? ((s_pitch_of(ns) * (2 * g.R + 1 + BH * (VS - 1)) * 4 + 127) & ~127) : 0;
+    const int stile = FORM >= 2 ? ((s_pitch_of(ns) * (2 * g.R + 1 + BH * (VS - 1)) * 4 + 127) & ~127) : 0;
     return (win + ns * SW * BH * VS + stile + ns * NSUB * VS * 8 + 127) & ~127;
   };
   for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
     const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
     if (wb > 256 || ns * SW > 256) break;
-    if (FORM == 2 && s_pitch_of(ns) > 256) break;
+    if (FORM >= 2 && s_pitch_of(ns) > 256) break;
     if (2 * stage_size(ns) + static_smem > plan->max_smem) break;
     if (plan->ns_override > 0 && ns != plan->ns_override) continue;
     const long long items = rows_total * ((p.strips_per_row + ns - 1) / ns);
@@ -1082,6 +1117,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       const int want = (nc + parts - 1) / parts;
       int m = (want - 1 + BH - 1) / BH;
       if (m > (nc - 1) / BH) m = (nc - 1) / BH;
+      if (FORM == 3 && m > kMaxM16) m = kMaxM16;   // as decode_item does
       const int L = m * BH + 1;
       const int nparts = (nc + L - 1) / L;
       const long long chunks = ((long long)ns * nc * nparts + 31) / 32;
@@ -1115,7 +1151,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.out = o;
   // peer stores from inside the kernel exist for the two default formulations on full-width
   // frames; other launches leave the peers to the caller's store kernel
-  constexpr bool kPeerVariant = FORM >= 1 && !PW && VS == 1;
+  constexpr bool kPeerVariant = FORM >= 1 && FORM != 3 && !PW && VS == 1;
   const bool peer = kPeerVariant && plan->npeer > 0;
   p.npeer = peer ? plan->npeer : 0;
   for (int q = 0; q < p.npeer; q++) p.peer[q] = plan->peer[q];
@@ -1149,7 +1185,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   // FORM 2: build the energy tables for the rows this launch needs (stream-ordered scratch)
   CUtensorMap map_s = map_ref, map_sh = map_ref;  // placeholders for the other formulations
   uint32_t *d_s = nullptr;
-  if (FORM == 2) {
+  if (FORM >= 2) {
     constexpr int BW = SW / NSUB;
     const int tp = (g.W + 3) & ~3;  // table pitch in elements
     const int full_rows = g.H / g.B;
@@ -1167,14 +1203,14 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     if (nfull > 0) {
       dim3 eg((tp + kEx - 1) / kEx, (nfull + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH, y_lo, nfull, d_s, tp,
-                                           per_pair, BH == 8 ? kBias8 : 0u);
+                                           per_pair, BH == 8 ? kBias8 : (FORM == 3 ? kBias16 : 0u));
       plan->kernels_launched++;
     }
     if (nhalf > 0) {
       dim3 eg((tp + kEx - 1) / kEx, (nhalf + kEy - 1) / kEy, npairs);
       box_energy_kernel<<<eg, 256, 0, s>>>(f.ref, f.pitch, ref_pair_stride, g.W, g.H, BW, BH / 2,
                                            g.H - BH / 2 - g.R, nhalf, d_s + (size_t)tp * nfull, tp, per_pair,
-                                           BH == 8 ? kBias8 : 0u);
+                                           BH == 8 ? kBias8 : (FORM == 3 ? kBias16 : 0u));
       plan->kernels_launched++;
     }
     e = cudaGetLastError();
@@ -1266,10 +1302,10 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
     if ((g.W % (4 * WORDS)) != 0)
       return launch_shape_pw<WORDS, BH, NSUB, 1, true>(plan, g, f, npairs, o, by_begin, by_count, s, err);
   }
-  if constexpr (FORM == 2) {
+  if constexpr (FORM >= 2) {
     // the energy table only knows full-width blocks, and its tile must fit the stage twice
     if (g.W % (4 * WORDS / NSUB) == 0) {
-      cudaError_t e = launch_shape_pw<WORDS, BH, NSUB, 2, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
+      cudaError_t e = launch_shape_pw<WORDS, BH, NSUB, FORM, false>(plan, g, f, npairs, o, by_begin, by_count, s, err);
       if (e != cudaErrorInvalidConfiguration) return e;
       (void)cudaGetLastError();
     }
@@ -1328,7 +1364,13 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
       }
       if (e == cudaSuccess && t1 > pb) e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, pb, t1 - pb, s, err);
     } else if (table) {
-      if (g.B == 16) e = launch_shape<4, 16, 1, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+      // 16x16: FORM 3 (table with the bias, no sum cur^2 in the tasks) unless the field also goes to peers
+      // (that publish path belongs to FORM 2) or ME_B200_FORM16=2 asks for the plain table (A/B measurements)
+      const char *f16 = getenv("ME_B200_FORM16");
+      const bool form16_plain = f16 && f16[0] == '2';
+      if (g.B == 16 && plan->npeer == 0 && !form16_plain)
+        e = launch_shape<4, 16, 1, 3>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
+      else if (g.B == 16) e = launch_shape<4, 16, 1, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
       else e = launch_shape<4, 8, 2, 2>(plan, g, f, npairs, o, r0, t1 - r0, s, err);
     } else if (plan->form >= 1) {
       if (g.B == 16) e = launch_shape<4, 16, 1, 1>(plan, g, f, npairs, o, r0, t1 - r0, s, err);

@@ -64,7 +64,9 @@ _LIB: Optional[C.CDLL] = None
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libme_b200.so")
+    # ME_B200_LIBRARY: another build of the same library (A/B experiments with tools/quick_bench.py)
+    return os.environ.get("ME_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                             "libme_b200.so")
 
 
 def load_library() -> C.CDLL:

@@ -135,9 +135,14 @@ def test_small_span_full_size(orc, R):
 # tuned-kernel formulations (env ME_B200_FORM, read when the context is created): default = energy
 # table for big launches / on-the-fly energies for small ones; "2" forces the table, "1" forces
 # on-the-fly, "0" = VABSDIFF4 + IDP.4A
-@pytest.mark.parametrize("form", ["2", "1", "0"])
+@pytest.mark.parametrize("form", ["2", "2plain", "1", "0"])
 @pytest.mark.parametrize("B,R,W,H", RANDOM_GEOMS)
 def test_random_differential_formulations(orc, monkeypatch, B, R, W, H, form):
+    if form == "2plain":    # 16x16: the table without the bias (FORM 2; the default table formulation is FORM 3)
+        if B != 16:
+            pytest.skip("only 16x16 blocks have two table formulations")
+        monkeypatch.setenv("ME_B200_FORM16", "2")
+        form = "2"
     monkeypatch.setenv("ME_B200_FORM", form)
     monkeypatch.setenv("ME_B200_PAIR", "1")   # 8x8 with the table: the pair kernel wherever rows can be paired
     test_random_differential(orc, B, R, W, H, me.ME_KERNEL_AUTO)
