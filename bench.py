@@ -48,8 +48,8 @@ WORKLOADS = {
     "4k_8x8_pm12": (3840, 2160, 8, 12, 16, "reference's own published runs: synthetic 3840x2160 luma, 8x8 blocks, full search +-12"),
     # the memory-bound end (north_star's "memory-bound small-range cases"): the
     # only candidate is the co-located block, one streaming pass over both frames
-    "1080p_16x16_pm0": (1920, 1080, 16, 0, 64, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-0"),
-    "4k_16x16_pm0": (3840, 2160, 16, 0, 32, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-0"),
+    "1080p_16x16_pm0": (1920, 1080, 16, 0, 256, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-0"),
+    "4k_16x16_pm0": (3840, 2160, 16, 0, 64, "memory-bound small-range case: synthetic 3840x2160 luma, 16x16 blocks, +-0"),
     "1080p_16x16_pm1": (1920, 1080, 16, 1, 256, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-1"),
     "1080p_16x16_pm2": (1920, 1080, 16, 2, 256, "memory-bound small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-2"),
     "1080p_16x16_pm4": (1920, 1080, 16, 4, 256, "small-range case: synthetic 1920x1080 luma, 16x16 blocks, +-4"),

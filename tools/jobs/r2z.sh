@@ -13,7 +13,7 @@ for w in 1080p_16x16_pm0 4k_16x16_pm0 1080p_16x16_pm1 1080p_16x16_pm2 1080p_16x1
 python tools/int_peaks.py > $out/int_peaks.json 2>&1
 CMD="python bench.py --steps 2 --warmup 3 --pairs 8 --no-cpu-baseline --sustained-s 0 --dropin-calls 0 --no-post --no-parity-check"
 $CMD > $out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv $CMD > $out/ncu_launches.log 2>&1
-$CMD > $out/plain_bench2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tiled_search -s 6 -c 1 -o $out/prof_tiled_final $CMD > $out/ncu_full.log 2>&1
+$CMD > $out/plain_bench2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tiled_search -s 3 -c 1 -o $out/prof_tiled_final $CMD > $out/ncu_full.log 2>&1
 python tools/quick_bench.py 3840 2160 16 1 32 > $out/plain_r1_4k.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:stream_search -s 3 -c 1 -o $out/prof_stream_pm1_4k python tools/quick_bench.py 3840 2160 16 1 32 > $out/ncu_r1.log 2>&1
 for f in $out/bench/*.json; do python - "$f" <<'PY'
 import json,sys
