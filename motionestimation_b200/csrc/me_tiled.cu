@@ -23,8 +23,8 @@
 //       the candidate column by WORDS funnel shifts on the otherwise idle ALU pipe)
 //       is scored against all BH current rows, feeding BH live candidates whose
 //       accumulators rotate through a register file of BH slots (the period-BH
-//       loop is fully unrolled so every index is static).  Three exact integer
-//       formulations of the SSD are compiled (template FORM; 2 is the default):
+//       loop is fully unrolled so every index is static).  Four exact integer
+//       formulations of the SSD are compiled (template FORM; 3 / 2 are the defaults):
 //         FORM 1  SSD = sum cur^2 + sum ref^2 - 2 sum cur*ref: one IDP.4A.U8.U8
 //                per 4 pixels for the cross term; sum ref^2 over the candidate's rows is a
 //                sliding sum of per-row IDP.4A(ref,ref), sum cur^2 is per task.  Half the
@@ -37,6 +37,9 @@
 //                TMA load), so a finished candidate costs one LDS instead of 4 IDP.4A per row
 //                step.  Used when the geometry has no partial-width blocks and the bigger stage
 //                still fits twice; otherwise FORM 1.
+//         FORM 3 (default for 16x16 blocks)  FORM 2 with the biased finish described below for 8x8
+//                blocks: table = E + 2^24, ranking key t = table - 2*dot, per-thread key t << 7 | dy_rel,
+//                per-block key t << 24 | dy << 16 | dx; sum cur^2 is added once per block at publish.
 //         FORM 0  |cur-ref| then square: VABSDIFF4.U8 (ALU pipe) + IDP.4A.U8.U8 (FMA pipe)
 //                per 4 pixels; kept for A/B measurements (env ME_B200_FORM=0), full blocks only.
 //     * a candidate that has seen its BH rows is folded into the thread's running
