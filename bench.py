@@ -564,18 +564,24 @@ def main():
         bw = [float(v[0].item()) for v in allv]
         nd = [float(v[1].item()) for v in allv]
         del pd
-        # deterministic greedy pairing, the same on every rank: most starved rank first, donor with most spare
+        # deterministic greedy pairing, the same on every rank: most starved rank first, donor with most spare.
+        # The detour is sized to the deficit (rounded, not rounded up) and never takes more than 80 % of the
+        # donor's spare link rate: a donor driven to 100 % of its own link becomes the slowest rank itself
+        # (measured: 4 of 16 pairs over donors with 7.4 GB/s spare made the 8-GPU end-to-end rate 4 % worse).
         frac = {r: 1.0 - 0.96 * bw[r] / nd[r] for r in range(world)}      # share of the bytes that must detour
-        spare = {r: bw[r] - 1.03 * nd[r] for r in range(world)}
+        spare = {r: bw[r] - nd[r] for r in range(world)}
+        hp_force = int(os.environ.get("BENCH_INGEST_HP", "0"))            # experiments: pairs per submit to detour
         helpers = {}
         for r in sorted((r for r in range(world) if frac[r] > 0.0), key=lambda r: -frac[r]):
-            hp = int(np.ceil(slot_pairs * frac[r]))
-            if hp >= slot_pairs:
+            donors = [d for d in range(world) if d != r and frac[d] <= 0.0 and d not in (h[0] for h in helpers.values())]
+            if not donors:
                 continue
-            donors = [d for d in range(world) if d != r and d not in (h[0] for h in helpers.values())
-                      and spare[d] >= hp / slot_pairs * nd[r]]
-            if donors:
-                d = max(donors, key=lambda d: spare[d])
+            d = max(donors, key=lambda d: spare[d])
+            hp = max(1, int(round(slot_pairs * frac[r])))
+            hp = min(hp, int(0.8 * spare[d] / nd[r] * slot_pairs), slot_pairs - 1)
+            if hp_force > 0:
+                hp = min(hp_force, slot_pairs - 1)
+            if hp >= 1:
                 helpers[r] = (d, hp)
         helper_error = None
         if rank in helpers:

