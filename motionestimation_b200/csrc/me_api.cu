@@ -989,8 +989,9 @@ PackPool *g_pack_pool = nullptr;  // created on the first drop-in call, under g_
 
 PackPool *pack_pool() {
   if (!g_pack_pool) {
-    int n = (int)std::thread::hardware_concurrency() - 1;
-    if (n > 6) n = 6;
+    // measured on the 16-core B200 hosts (tools/dropin_sweep.py, 1080p): 6 workers 0.385 ms per call, 10 0.372, 14 0.366
+    int n = (int)std::thread::hardware_concurrency() - 2;
+    if (n > 10) n = 10;
     if (const char *e = getenv("ME_B200_PACK_THREADS")) n = atoi(e);
     if (n < 0) n = 0;
     if (n > 32) n = 32;
@@ -1096,12 +1097,21 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
     ME_CUDA(ctx, cudaMemset(ctx->d_arrive, 0, 256));
     ME_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_arrive, sizeof(unsigned int) * (kMaxChunks + 1), cudaHostAllocDefault));
   }
+  // Arriving-frame launches send the REFERENCE frame first, whole (two pieces, so that the upload starts when half
+  // of it is narrowed): once it is resident the energy-table pre-pass can run, and the search of the arriving
+  // current frame is the table formulation (FORM 2 / 3: 203 instead of ~240 us for a 1080p pair) -- the reference
+  // upload costs less than that difference.  ME_B200_DROPIN_REF_FIRST=0: the interleaved order (reference rows
+  // travel with the band that needs them, FORM 1).
+  bool ref_first = arrive;
+  if (const char *e = getenv("ME_B200_DROPIN_REF_FIRST")) ref_first = ref_first && e[0] != '0';
+  const int nrefc = ref_first ? 2 : 0;            // chunks that carry only reference rows
+  if (nrefc + nbands > kMaxChunks) nbands = kMaxChunks - nrefc;
   PackJob job;
   job.src[0] = refFrame; job.src[1] = pf->frame;
   job.dst[0] = ctx->h_ref; job.dst[1] = ctx->h_cur;
   job.row_elems = (size_t)W;
   job.rows = H;
-  job.nchunks = nbands;
+  job.nchunks = nrefc + nbands;
   {
     // pieces of >= 64 KB (narrowed), one per worker + the calling thread at most
     int sub = pool->workers() + 1;
@@ -1114,25 +1124,36 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   for (int c = 0; c <= nbands; c++) {
     band_row[c] = (int)((long long)nby * c / nbands);
     const int y = c == nbands ? H : (band_row[c] * B < H ? band_row[c] * B : H);
-    job.row0[1][c] = y;                                                       // current frame: the band's own rows
-    job.row0[0][c] = c == 0 ? 0 : (y + extraSpan < H ? y + extraSpan : H);    // reference: + R rows of halo below
+    job.row0[1][nrefc + c] = y;                                               // current frame: the band's own rows
+    // reference: + R rows of halo below (reference first: nothing left for the band chunks)
+    job.row0[0][nrefc + c] = ref_first ? H : (c == 0 ? 0 : (y + extraSpan < H ? y + extraSpan : H));
   }
-  job.row0[0][nbands] = H;
+  job.row0[0][nrefc + nbands] = H;
+  for (int c = 0; c < nrefc; c++) {                                           // reference-only chunks
+    job.row0[0][c] = (int)((long long)H * c / nrefc);
+    job.row0[1][c] = 0;
+  }
+  unsigned int arrive_base = 0;
+  if (arrive) {
+    ctx->arrive_epoch = (ctx->arrive_epoch + 1) & 0x7fffu;
+    if (ctx->arrive_epoch == 0) {
+      // the 15-bit epoch wrapped: a flag left over from 32768 calls ago must not look like "rows resident"
+      ctx->arrive_epoch = 1;
+      ME_CUDA(ctx, cudaMemset(ctx->d_arrive, 0, sizeof(unsigned int)));
+    }
+    arrive_base = ctx->arrive_epoch << 16;
+  }
   pool->start(job);
   cudaError_t ce = cudaSuccess;
   rc = ME_OK;
   me::Frames fr{sl.d_cur, sl.d_ref, ctx->pitch, ctx->frame_bytes};
   me::Out out{sl.d_mvx, sl.d_mvy, sl.d_ssd, sl.d_score};
-  unsigned int arrive_base = 0;
-  if (arrive) {
-    ctx->arrive_epoch = (ctx->arrive_epoch + 1) & 0x7fffu;
-    arrive_base = ctx->arrive_epoch << 16;
-    for (int c = 0; c < nbands; c++) ctx->h_arrive[c] = arrive_base + (unsigned int)job.row0[1][c + 1];
-  }
-  for (int c = 0; c < nbands && ce == cudaSuccess && rc == ME_OK; c++) {
+  for (int c = 0; c < nbands && arrive; c++) ctx->h_arrive[c] = arrive_base + (unsigned int)job.row0[1][nrefc + c + 1];
+  for (int cc = 0; cc < nrefc + nbands && ce == cudaSuccess && rc == ME_OK; cc++) {
+    const int c = cc - nrefc;   // band index; negative: a reference-only chunk
     for (int f = 0; f < 2 && ce == cudaSuccess; f++) {
-      pool->wait_chunk(2 * c + f);
-      const int r0 = job.row0[f][c], nr = job.row0[f][c + 1] - r0;
+      pool->wait_chunk(2 * cc + f);
+      const int r0 = job.row0[f][cc], nr = job.row0[f][cc + 1] - r0;
       if (nr <= 0) continue;
       uint8_t *d = (f == 0 ? sl.d_ref : sl.d_cur) + (size_t)r0 * ctx->pitch;
       const uint8_t *h = job.dst[f] + (size_t)r0 * W;
@@ -1141,20 +1162,22 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
       else
         ce = cudaMemcpy2DAsync(d, ctx->pitch, h, W, W, nr, cudaMemcpyHostToDevice, copy_stream);
     }
-    if (trace) t_band[c] = getTimeStamp();
+    if (trace) t_band[cc] = getTimeStamp();
     if (arrive) {
       // rows of band c (and the reference rows R below) are resident once this 4-byte copy has run
-      if (ce == cudaSuccess)
+      if (c >= 0 && ce == cudaSuccess)
         ce = cudaMemcpyAsync(ctx->d_arrive, ctx->h_arrive + c, sizeof(unsigned int), cudaMemcpyHostToDevice, copy_stream);
-      if (c == 0 && ce == cudaSuccess) {
+      // the launch goes out behind the first band -- or, reference first, behind the last reference chunk (the
+      // kernel then waits for the current frame's rows on the device)
+      if (cc == (ref_first ? nrefc - 1 : 0) && ce == cudaSuccess) {
         ce = cudaEventRecord(ctx->band_events[0], copy_stream);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sl.stream, ctx->band_events[0], 0);
         if (ce == cudaSuccess && !(pool->bad_bits() & ~0xffu)) {
-          me::tiled_plan_set_arrive(ctx->plan, ctx->d_arrive, arrive_base, (int *)(ctx->d_arrive + 1));
+          me::tiled_plan_set_arrive(ctx->plan, ctx->d_arrive, arrive_base, (int *)(ctx->d_arrive + 1), ref_first);
           rc = run_search(ctx, fr, 1, 0, nby, out, sl.stream);
         }
       }
-      if (trace) t_launch[c] = getTimeStamp();
+      if (trace) t_launch[cc] = getTimeStamp();
       continue;
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(ctx->band_events[c], copy_stream);
@@ -1194,8 +1217,8 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   }
   if (trace) {
     const double t_done = getTimeStamp();
-    fprintf(stderr, "[me_b200 trace] bands %d:", nbands);
-    for (int c = 0; c < nbands; c++)
+    fprintf(stderr, "[me_b200 trace] reference chunks %d, bands %d:", nrefc, nbands);
+    for (int c = 0; c < nrefc + nbands; c++)
       fprintf(stderr, " [%d up %.0f launched %.0f]", c, (t_band[c] - t_entry) * 1e6, (t_launch[c] - t_entry) * 1e6);
     fprintf(stderr, " done %.0f us\n", (t_done - t_entry) * 1e6);
   }

@@ -63,8 +63,11 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
 // uploaded top to bottom.  *flag (device memory) = base + number of current-frame rows resident, with the
 // reference rows R below them; the uploader advances it in stream order after each piece.  Items wait for
 // their rows; *status becomes 1 if one gave up after ~1 s.  (nullptr switches it off.)
+// ref_resident: the WHOLE reference frame is already on the device (only the current frame is arriving) -- then the
+// energy-table formulations (pre-pass over the reference frame + FORM 2 / 3) may serve the launch.
 bool tiled_arrive_supported(const Geom &g);
-void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status);
+void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status,
+                           bool ref_resident = false);
 
 // SSIM cost on the tiled kernel (me_tiled.cu, FORM 4): full-height, full-width 16x16 block rows; the caller supplies
 // the statistics tables ({pixel sum, stddev bits} per reference rectangle, row pitch W entries, and per current

@@ -79,7 +79,10 @@ namespace {
 #endif
 constexpr int kWarps = ME_WARPS;
 constexpr int kThreads = kWarps * 32;
-constexpr int kMaxStages = 4;
+#ifndef ME_MAX_STAGES
+#define ME_MAX_STAGES 4
+#endif
+constexpr int kMaxStages = ME_MAX_STAGES;
 constexpr int kWinPitch = 256;  // window row pitch in shared memory = TMA box width (the maximum);
                                 // a compile-time pitch turns every row offset into an LDS immediate
 constexpr uint32_t kNoKey = 0xffffffffu;
@@ -1113,6 +1116,7 @@ struct TiledPlan {
   const unsigned int *arrive_flag = nullptr;
   unsigned int arrive_base = 0;
   int *arrive_status = nullptr;
+  bool arrive_ref_resident = false;   // the whole reference frame is resident: the energy-table formulations may run
   // FORM 4 (SSIM cost; launch_tiled_ssim16): the statistics tables the caller built
   const int2 *ssim_table = nullptr;      // {pixel sum, stddev bits} per 16x16 rectangle of the reference frame
   int ssim_y_lo = 0, ssim_rows = 0;      // frame row of the table's first row, rows per pair
@@ -1184,8 +1188,10 @@ int tiled_plan_set_peers(TiledPlan *plan, const Out *peers, int npeers) {
   return 0;
 }
 
-void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status) {
+void tiled_plan_set_arrive(TiledPlan *plan, const unsigned int *flag, unsigned int base, int *status,
+                           bool ref_resident) {
   if (!plan) return;
+  plan->arrive_ref_resident = ref_resident;
   plan->arrive_flag = flag;
   plan->arrive_base = base;
   plan->arrive_status = status;
@@ -1432,7 +1438,9 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     if constexpr (kPeerVariant) {
       if (peer) kern = tiled_search_kernel<WORDS, BH, NSUB, FORM, PW, true>;
     }
-    if constexpr (FORM == 1) {
+    // arriving-frame instantiations: FORM 1 (any geometry), and the table formulations for full-width frames whose
+    // reference frame is already resident (the pre-pass above ran on it)
+    if constexpr (FORM == 1 || ((FORM == 3 || (FORM == 2 && BH == 8)) && !PW)) {
       if (plan->arrive_flag && !peer) {
         p.arrive_flag = plan->arrive_flag;
         p.arrive_base = plan->arrive_base;
@@ -1533,7 +1541,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   plan->outputs_enqueued = false;
   struct ArriveReset {   // the arriving-frame settings apply to this launch only
     TiledPlan *p;
-    ~ArriveReset() { p->arrive_flag = nullptr; p->arrive_status = nullptr; }
+    ~ArriveReset() { p->arrive_flag = nullptr; p->arrive_status = nullptr; p->arrive_ref_resident = false; }
   } arrive_reset{plan};
   const int full_rows = g.H / g.B;
   const int hrem = g.H % g.B;
@@ -1543,7 +1551,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
   cudaError_t e = cudaSuccess;
   if (t1 > r0) {
     // the energy-table pre-pass (two small launches) only pays off once there is enough work
-    const bool table = plan->form == 2 && !plan->arrive_flag &&
+    const bool table = plan->form == 2 && (!plan->arrive_flag || plan->arrive_ref_resident) &&
                        (long long)npairs * g.W * g.H >= (plan->form_env_forced ? 0 : 2000000LL);
     // 8x8 blocks with the energy table on full-width frames: block rows whose window is not clamped
     // vertically go through the pair kernel two at a time, the rest through the single-row kernel
@@ -1553,7 +1561,7 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
     const bool pair_pays = g.H >= 1440 || g.R <= 8 || g.R >= 48;
     const char *pe = getenv("ME_B200_PAIR");   // 0 / 1 force it off / on (measurements, tests)
     const bool want_pair = pe ? pe[0] == '1' : pair_pays;
-    if (table && want_pair && g.B == 8 && g.W % 8 == 0 && plan->npeer == 0) {
+    if (table && want_pair && g.B == 8 && g.W % 8 == 0 && plan->npeer == 0 && !plan->arrive_flag) {
       const int first = (g.R + 7) / 8;                        // y0 >= R
       const int last = (g.H - g.R - 16) / 8;                  // y0 + 16 + R <= H  (upper row of the last pair)
       pa = r0 > first ? r0 : first;

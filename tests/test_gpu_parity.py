@@ -188,17 +188,19 @@ def test_drop_in_prediction_frame(orc):
     assert ei.value.code == me.ME_ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("mode", ["arrive", "bands", "one"])
+@pytest.mark.parametrize("mode", ["arrive", "arrive_interleaved", "bands", "one"])
 @pytest.mark.parametrize("W,H,B,R", [(1920, 1080, 16, 32), (1930, 1080, 16, 12), (1920, 1080, 8, 12), (1280, 1000, 16, 20),
                                      (3840, 2160, 8, 12)])
 def test_drop_in_large_frames_pipelined(orc, monkeypatch, W, H, B, R, mode):
     """me_b200_search on frames large enough for the pipelined ingest: the int frames are narrowed by the
     worker threads and uploaded band by band while the search already runs -- as ONE launch whose items wait
-    for their rows ("arrive": the tuned kernel with the on-the-fly energies; needs every block row on that
-    kernel, so 1280x1000 with its odd bottom row runs banded instead), as one launch per band ("bands") or
-    after the whole upload ("one").  Every block against the oracle, twice per mode (the arrival flag is
+    for their rows ("arrive": the reference frame travels first, whole, and the search is the energy-table
+    formulation, FORM 2 / 3 -- FORM 1 for the partial-width 1930; "arrive_interleaved": reference rows travel with
+    the band that needs them, on-the-fly energies; both need every block row on the tuned kernel, so 1280x1000 with
+    its odd bottom row runs banded instead), as one launch per band ("bands") or after the whole upload ("one").  Every block against the oracle, twice per mode (the arrival flag is
     reused across calls), scores and SSDs included."""
-    monkeypatch.setenv("ME_B200_DROPIN_ARRIVE", "1" if mode == "arrive" else "0")
+    monkeypatch.setenv("ME_B200_DROPIN_ARRIVE", "1" if mode.startswith("arrive") else "0")
+    monkeypatch.setenv("ME_B200_DROPIN_REF_FIRST", "0" if mode == "arrive_interleaved" else "1")
     if mode == "one":
         monkeypatch.setenv("ME_B200_DROPIN_BANDS", "1")
     me.load_library().me_b200_release_cached()
