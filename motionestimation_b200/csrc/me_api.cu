@@ -1100,10 +1100,13 @@ int dropin_search(predictionFrame *pf, const int *refFrame, int extraSpan, int c
   // Arriving-frame launches send the REFERENCE frame first, whole (two pieces, so that the upload starts when half
   // of it is narrowed): once it is resident the energy-table pre-pass can run, and the search of the arriving
   // current frame is the table formulation (FORM 2 / 3: 203 instead of ~240 us for a 1080p pair) -- the reference
-  // upload costs less than that difference.  ME_B200_DROPIN_REF_FIRST=0: the interleaved order (reference rows
-  // travel with the band that needs them, FORM 1).
-  bool ref_first = arrive;
-  if (const char *e = getenv("ME_B200_DROPIN_REF_FIRST")) ref_first = ref_first && e[0] != '0';
+  // upload can cost less than that difference.  Otherwise the interleaved order: reference rows travel with the
+  // band that needs them, FORM 1.
+  // Default: 8x8 blocks only.  Same-box A/B (tools/jobs/r3h.sh): 4K 8x8 +-12 1.74 -> 1.55 ms per call, but 16x16 blocks
+  // gain nothing (1080p +-32 0.370 vs 0.375, 4K +-32 1.27 vs 1.25 ms): FORM 1 is closer to FORM 3 there than the later
+  // launch costs.  ME_B200_DROPIN_REF_FIRST=1 / 0 forces it on (any block size) / off.
+  bool ref_first = arrive && B == 8;
+  if (const char *e = getenv("ME_B200_DROPIN_REF_FIRST")) ref_first = arrive && e[0] != '0';
   const int nrefc = ref_first ? 2 : 0;            // chunks that carry only reference rows
   if (nrefc + nbands > kMaxChunks) nbands = kMaxChunks - nrefc;
   PackJob job;

@@ -188,6 +188,15 @@ __device__ __forceinline__ Item decode_item(const TiledParams &p, int it) {
   return I;
 }
 
+// period kind of the streaming loop as a compile-time tag or a run-time flag (see period_body)
+template <bool V>
+struct BoolTag {
+  static constexpr bool value = V;
+};
+struct BoolRt {
+  bool value;
+};
+
 // ---------------------------------------------------------------- the kernel
 template <int WORDS, int BH, int NSUB, int FORM, bool PW, bool PEER, bool ARRIVE = false>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -478,9 +487,11 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       const int s_pitch = p.s_pitch;
       const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * s_pitch +
                             p.e_s + st * SW + dx;
-      for (int per = 0; per <= m_uni; per++) {
-        const bool first = per == 0;
-        const bool last = per == m_uni;
+      // one period of BH steps.  first_c / last_c are plain bools (one code copy whose ramp branches are warp-uniform
+      // run-time branches: BoolRt) or compile-time tags (BoolTag: a copy per period kind without those branches)
+      auto period_body = [&](const auto first_c, const auto last_c) {
+        const bool first = first_c.value;
+        const bool last = last_c.value;
         if constexpr (FORM == 4)   // the block's best score so far, whoever found it (+inf stays +inf)
           thr4 = fmaxf(thr4, __uint_as_float((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&best[st]) >> 32)));
 #pragma unroll
@@ -599,6 +610,26 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         }
         dy_fin += BH;
         if constexpr (FORM == 4) drain4();
+      };
+#ifndef ME_SPLIT_PERIODS
+#define ME_SPLIT_PERIODS 1
+#endif
+      if constexpr (ME_SPLIT_PERIODS && BH == 8 && (FORM == 1 || FORM == 2) && !PEER) {
+        // 8x8 blocks: a step holds only 32 IDP.4A, so the two ramp branches per step show (ncu: 0.5 stall cycles per
+        // issued instruction in branch_resolving, profiles/ncu_tiled_8x8_pm12_r02_*).  The three period kinds get
+        // their own unrolled copy (7.5 KB each or less: the instruction cache holds them).  Measured: 4K 8x8 +-12
+        // 49.4 -> 54.9 %, +-32 67.5 -> 74.6 %, Foreman CIF 40.3 -> 43.4 % of the peak.  16x16 keeps its single 25 KB
+        // copy: with two or four copies FORM 3 ran 3.6x SLOWER (22.7 % instead of 81.2 %; not investigated
+        // further -- instruction-cache capacity or spills in the bigger function).
+        if (m_uni == 0) {
+          period_body(BoolTag<true>{}, BoolTag<true>{});
+        } else {
+          period_body(BoolTag<true>{}, BoolTag<false>{});
+          for (int per = 1; per < m_uni; per++) period_body(BoolTag<false>{}, BoolTag<false>{});
+          period_body(BoolTag<false>{}, BoolTag<true>{});
+        }
+      } else {
+        for (int per = 0; per <= m_uni; per++) period_body(BoolRt{per == 0}, BoolRt{per == m_uni});
       }
 
       // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
@@ -1558,7 +1589,10 @@ cudaError_t launch_tiled(TiledPlan *plan, const Geom &g, const Frames &f, int np
     int pa = t1, pb = t1;   // block rows [pa, pb) run as pairs
     // Measured (profiles/README.md): +12 % at +-8, +6 % at +-64, +1..2 % at +-12 / +-32 on 4K frames, but -1..-3 %
     // on 1080p / CIF frames at +-12 -- so: 4K-class frames and the spans where it clearly wins
-    const bool pair_pays = g.H >= 1440 || g.R <= 8 || g.R >= 48;
+    // ... all of that BEFORE the single-row kernel got one unrolled copy per period kind (ME_SPLIT_PERIODS): since
+    // then it beats the pair kernel everywhere (4K +-12 54.9 vs 49.7 %, +-32 74.6 vs 67.5 %, Foreman CIF 43.4 vs 37.9 %
+    // of the peak), so the pair kernel is opt-in (ME_B200_PAIR=1; the tests keep running it)
+    const bool pair_pays = false;
     const char *pe = getenv("ME_B200_PAIR");   // 0 / 1 force it off / on (measurements, tests)
     const bool want_pair = pe ? pe[0] == '1' : pair_pays;
     if (table && want_pair && g.B == 8 && g.W % 8 == 0 && plan->npeer == 0 && !plan->arrive_flag) {
