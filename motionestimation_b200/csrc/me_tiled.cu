@@ -9,7 +9,7 @@
 //   frame pair; a strip is NSUB adjacent blocks = 4*WORDS pixels wide.  All
 //   candidates of an item live in one macro window of (NS*4*WORDS + 2R) x
 //   (2R + BH) reference pixels.  A persistent CTA (one per SM, 16 warps, no
-//   dedicated producer) walks its items through a 2..4 stage shared-memory ring:
+//   dedicated producer) walks its items through a 2..8 stage shared-memory ring:
 //     * the macro window and the current-frame strip tile of an item arrive by TMA
 //       (cp.async.bulk.tensor, 3-D u8 tensor maps, one mbarrier per stage).  TMA only
 //       accepts 16-byte aligned inner coordinates (measured, tools/tma_probe.cu), so
@@ -40,6 +40,10 @@
 //         FORM 3 (default for 16x16 blocks)  FORM 2 with the biased finish described below for 8x8
 //                blocks: table = E + 2^24, ranking key t = table - 2*dot, per-thread key t << 7 | dy_rel,
 //                per-block key t << 24 | dy << 16 | dx; sum cur^2 is added once per block at publish.
+//         FORM 4 (opt-in, ME_B200_SSIM_FORM4=1)  the SSIM cost of me_ssim.cu on this kernel: the accumulators hold
+//                sum r*c, the table holds {pixel sum, stddev} per reference rectangle, a finished candidate takes a
+//                division-free bound and survivors are evaluated by all lanes together at the end of each period.
+//                Bit-exact, but measured slower than me_ssim.cu's streaming kernel (profiles/ssim_form4_r02.txt).
 //         FORM 0  |cur-ref| then square: VABSDIFF4.U8 (ALU pipe) + IDP.4A.U8.U8 (FMA pipe)
 //                per 4 pixels; kept for A/B measurements (env ME_B200_FORM=0), full blocks only.
 //     * a candidate that has seen its BH rows is folded into the thread's running
@@ -52,6 +56,8 @@
 //     * the last warp to leave an item writes the item's motion vectors / SSD /
 //       score (SoA), takes the next item from a launch-wide atomic counter (dynamic
 //       scheduling over all CTAs) and re-arms the stage with its TMA loads.
+//   8x8 blocks get one unrolled copy of the period per period kind (first / middle / last / single) instead of
+//   warp-uniform branches inside one copy: a step holds only 32 IDP.4A there and the branches showed in the profile.
 //   Vertical parts always hold m*BH + 1 candidates, so the ramp-up and ramp-down
 //   of the rotating accumulators have a static shape and are skipped with
 //   warp-uniform branches: no wasted pixel-compares, no validity tests in the loop.
@@ -80,7 +86,7 @@ namespace {
 constexpr int kWarps = ME_WARPS;
 constexpr int kThreads = kWarps * 32;
 #ifndef ME_MAX_STAGES
-#define ME_MAX_STAGES 4
+#define ME_MAX_STAGES 8
 #endif
 constexpr int kMaxStages = ME_MAX_STAGES;
 constexpr int kWinPitch = 256;  // window row pitch in shared memory = TMA box width (the maximum);
@@ -325,6 +331,8 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     const int L = I.m * BH + 1;
     const int ndx = 2 * p.R + 1;
 
+    // (Tried for 8x8 blocks and dropped: fetching the NEXT chunk index while the current chunk is being worked on --
+    // 1 to 4 % slower everywhere, the extra live value costs more than the hidden round trip.)
     for (;;) {
       int c = 0;
       if (lane == 0) c = (int)atomicAdd(&chunk_ctr[stage], 1u);
