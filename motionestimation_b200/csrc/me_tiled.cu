@@ -203,6 +203,18 @@ struct BoolRt {
   bool value;
 };
 
+// ME_TRACE_ITEMS (experiment builds only): per-item timeline in p.dbg[item * 8 + k], SM clock values:
+//   0 re-arm starts  1 item index known (global atomic back)  2 TMA loads issued  3 first warp sees the data
+//   4 last chunk handed out  5 last warp leaves (publish starts)  6 published   7 SM id
+#ifdef ME_TRACE_ITEMS
+#define ME_TRACE(item, k, how) do { if (p.dbg && (item) >= 0) how(p.dbg + (size_t)(item) * 8 + (k), (unsigned long long)clock64()); } while (0)
+__device__ __forceinline__ void trace_set(unsigned long long *a, unsigned long long v) { *a = v; }
+__device__ __forceinline__ void trace_min(unsigned long long *a, unsigned long long v) { atomicMin(a, v); }
+__device__ __forceinline__ void trace_max(unsigned long long *a, unsigned long long v) { atomicMax(a, v); }
+#else
+#define ME_TRACE(item, k, how) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- the kernel
 template <int WORDS, int BH, int NSUB, int FORM, bool PW, bool PEER, bool ARRIVE = false>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -214,8 +226,11 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   constexpr int WPB = WORDS / NSUB;   // words per block row
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];  // TMA bytes of the stage's item have landed
-  __shared__ uint32_t chunk_ctr[kMaxStages];              // next 32-task chunk of the stage's item
-  __shared__ uint32_t left_ctr[kMaxStages];               // warps that are done with the stage's item
+  // ring: next chunk of the stage's item.  queue: generation << 22 | chunks of the item << 11 | chunks handed out -- one atomicAdd
+  // returns a consistent (generation, chunk count, chunk index) triple; a warp only waits for a stage's data after it
+  // has claimed a chunk of that generation, so it can never wait for a phase that is two re-arms old.
+  __shared__ uint32_t chunk_ctr[kMaxStages];
+  __shared__ uint32_t left_ctr[kMaxStages];               // queue: finished chunks of the item; ring: warps that left it
   __shared__ int item_id[kMaxStages];                     // item held by the stage, -1 = no more work
   __shared__ Item item_s[kMaxStages];                     // its decoded geometry (five integer divisions: decoded
                                                           // once by the re-arming warp, not by all 16 warps)
@@ -227,22 +242,49 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
   static_assert(FORM != 3 || (BH == 16 && NSUB == 1 && !PW && !PEER), "FORM 3 is the 16x16 table formulation");
   static_assert(FORM != 4 || (BH == 16 && NSUB == 1 && WORDS == 4 && !PW && !PEER && !ARRIVE), "FORM 4 is the 16x16 SSIM cost");
   constexpr int kSEntry = FORM == 4 ? 8 : 4;   // bytes per table entry (FORM 4: {pixel sum, stddev bits})
+  // Stage protocol.  kQueue (8x8 blocks): the stages are a work queue -- a warp claims a chunk wherever one is left and
+  // the warp that FINISHES an item's last chunk publishes it and re-arms the stage.  Otherwise (16x16): the lock-step
+  // ring of round 1 -- every warp passes every item, the last one to leave re-arms.  Measured (late round 2, same
+  // box): the queue is worth +5 % where items hold fewer chunks than the CTA has warps (4K 8x8 +-12 54.7 -> 57.4 %,
+  // Foreman CIF 44.0 -> 46.5 %, 16x16 +-8 37.4 -> 39.6 %) and costs 1 to 2 % where chunks are long (16x16 +-32 81.2
+  // -> 80.2 %, +-64 76.8 -> 75.0 %: two more shared-memory round trips per chunk), so each block size keeps the
+  // protocol that is faster on the BASELINE configurations.
+#ifndef ME_QUEUE_ALL
+#define ME_QUEUE_ALL 0
+#endif
+  constexpr bool kQueue = BH == 8 || ME_QUEUE_ALL;
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
   // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
   // row-major order, so the cheap clamped/half-height bottom rows come last and the tail is
   // short), reset the stage's keys and counters and start the TMA.  When the work is exhausted the
   // stage is marked dead and its barrier completed without a load.  Called by one whole warp.
-  auto refill = [&](const int stage) {
+  auto refill = [&](const int stage, const uint32_t gen) {
     uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
     int it = 0;
+#ifdef ME_TRACE_ITEMS
+    const unsigned long long t_rearm = clock64();
+#endif
     if (lane == 0) it = (int)atomicAdd(p.next_item, 1u);
     it = __shfl_sync(0xffffffffu, it, 0);
+#ifdef ME_TRACE_ITEMS
+    if (p.dbg && lane == 0 && it < p.total_items) {
+      p.dbg[(size_t)it * 8 + 0] = t_rearm;
+      p.dbg[(size_t)it * 8 + 1] = clock64();
+      p.dbg[(size_t)it * 8 + 3] = ~0ull;
+      p.dbg[(size_t)it * 8 + 4] = 0ull;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.dbg[(size_t)it * 8 + 7] = smid;
+    }
+#endif
     if (it >= p.total_items) {
+      // queue: the hand-out word stays exhausted, nobody claims from, or waits for, a dead stage;
+      // ring: the waiting warps are released by completing the phase without a load
       if (lane == 0) {
-        item_id[stage] = -1;
-        mbar_arrive_expect_tx(&full_bar[stage], 0);
+        *reinterpret_cast<volatile int *>(&item_id[stage]) = -1;
+        if (!kQueue) mbar_arrive_expect_tx(&full_bar[stage], 0);
       }
       __syncwarp();
       return;
@@ -251,7 +293,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     for (int b = lane; b < nblk_item; b += 32)   // FORM 4 keeps a maximum
       best[b] = FORM == 4 ? (unsigned long long)p.dbg_thr_bits << 32 : ~0ull;
     if (lane == 0) {
-      chunk_ctr[stage] = 0;
+      if (!kQueue) chunk_ctr[stage] = 0;
       left_ctr[stage] = 0;
       item_id[stage] = it;
       item_s[stage] = I;
@@ -291,18 +333,28 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
         else
           tma_load_3d(sb + s_off, &map_sh, &full_bar[stage], I.strip0 * SW - p.R - p.e_s, 0, I.pair);
       }
+      ME_TRACE(it, 2, trace_set);
+      if (kQueue) {
+        // publish the item last: whoever claims a chunk from this word sees the geometry, the reset keys and counters
+        __threadfence_block();
+        atomicExch(&chunk_ctr[stage], ((gen & 0x3ffu) << 22) | ((uint32_t)I.nchunks << 11));
+      }
     }
     __syncwarp();
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; s++) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < kMaxStages; s++) {
+      mbar_init(&full_bar[s], 1);
+      chunk_ctr[s] = 0;   // nothing to hand out yet
+      item_id[s] = 0;     // ... but not dead either
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x < 32)
-    for (int k = 0; k < p.stages; k++) refill(k);
+    for (int k = 0; k < p.stages; k++) refill(k, 0u);
 
   // Optional start-up stagger of the warps that share a scheduler (env ME_B200_SKEW, cycles;
   // default 0 = off).  Measured: no effect on throughput -- the warps drift apart by themselves.
@@ -312,6 +364,82 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     }
   }
 
+  // Two stage protocols (kQueue picks one per instantiation; the chunk work and the publish code are shared text,
+  // me_tiled_chunk.inc / me_tiled_publish.inc):
+  if constexpr (kQueue) {
+  // The stages are a work queue, not a lock-step ring: a warp walks over them and claims a chunk wherever one is
+  // left; the warp that FINISHES the last chunk of an item publishes it and re-arms the stage.  (Round 1 / early
+  // round 2 re-armed a stage when all 16 warps had passed it -- with items of fewer chunks than warps every item
+  // then waited for the slowest warp of the CTA: the per-item timeline, -DME_TRACE_ITEMS, showed stages waiting 2 to
+  // 4 chunk times for their last visitor.)  A stage whose re-arm found no more items is dead; the walk ends when
+  // all stages are dead.
+  uint32_t dead = 0, idle_ns = 100u;
+  bool progress = false;
+  for (int stage = 0; dead != (1u << p.stages) - 1u;) {
+    bool got = false;
+    if (!(dead & (1u << stage))) {
+      const uint32_t peek = *reinterpret_cast<volatile uint32_t *>(&chunk_ctr[stage]);
+      if ((peek & 0x7ffu) < ((peek >> 11) & 0x7ffu)) {
+        uint32_t word = 0;
+        if (lane == 0) word = atomicAdd(&chunk_ctr[stage], 1u);
+        word = __shfl_sync(0xffffffffu, word, 0);
+        const int c = (int)(word & 0x7ffu), nch = (int)((word >> 11) & 0x7ffu);
+        if (c < nch) {
+          got = true;
+          progress = true;
+          // (no fence needed here: the geometry and the reset keys were written before the re-arming thread's
+          // mbarrier arrive (release), and the try_wait below is the matching acquire)
+    uint8_t *sb = smem + (size_t)stage * p.stage_bytes;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sb + best_off);
+    mbar_wait(&full_bar[stage], (word >> 22) & 1u);
+    const int it = *reinterpret_cast<volatile int *>(&item_id[stage]);
+    const Item I = item_s[stage];
+    if (lane == 0) ME_TRACE(it, 3, trace_min);
+    if (lane == 0) ME_TRACE(it, 4, trace_max);
+
+    const int L = I.m * BH + 1;
+    const int ndx = 2 * p.R + 1;
+
+    {
+#include "me_tiled_chunk.inc"
+    // ---- chunk finished; the warp that finishes the last one publishes the item and re-arms the stage
+    __syncwarp();
+    int prev = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      prev = (int)atomicAdd(&left_ctr[stage], 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == nch - 1) {
+      __threadfence_block();
+      if (lane == 0) ME_TRACE(it, 5, trace_set);
+#include "me_tiled_publish.inc"
+      __syncwarp();
+      if (lane == 0) ME_TRACE(it, 6, trace_set);
+      refill(stage, (word >> 22) + 1u);
+    }
+        }  // claimed a chunk
+      } else if (*reinterpret_cast<volatile int *>(&item_id[stage]) < 0) {
+        dead |= 1u << stage;
+      }
+    }
+    if (!got) {
+      // next stage; after a whole lap without a chunk, back off briefly (the others are computing or loading)
+      // (exponential: a polling warp takes issue slots from the computing ones -- with a fixed 64 ns the long-chunk
+      // geometries lost 1 to 2 %)
+      if (++stage == p.stages) {
+        stage = 0;
+        if (!progress) {
+          __nanosleep(idle_ns);
+          idle_ns = idle_ns < 1600u ? idle_ns * 2u : idle_ns;
+        } else {
+          idle_ns = 100u;
+        }
+        progress = false;
+      }
+    }
+  }
+  } else {
   // Every warp walks the ring; a stage that reported "no more work" is never re-armed and is
   // skipped from then on; the walk ends when all stages are dead.
   uint32_t dead = 0;
@@ -327,6 +455,7 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       continue;
     }
     const Item I = item_s[stage];
+    if (lane == 0) ME_TRACE(it, 3, trace_min);
 
     const int L = I.m * BH + 1;
     const int ndx = 2 * p.R + 1;
@@ -338,337 +467,9 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
       if (lane == 0) c = (int)atomicAdd(&chunk_ctr[stage], 1u);
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c >= I.nchunks) break;
+      if (lane == 0) ME_TRACE(it, 4, trace_max);
 
-      // ---- decode this lane's task: (part, strip, dx); consecutive lanes = consecutive dx
-      int task = c * 32 + lane;
-      const bool active = task < I.ntasks;
-      task = min(task, I.ntasks - 1);
-      // task = (part * ns + strip) * ndx + dx; ndx divides by multiply-high (tasks < 2^16)
-      // (R = 0: ndx = 1 and 2^32 / 1 does not fit the multiplier -- inv_ndx is 0 and row = task)
-      const int row = p.inv_ndx ? (int)__umulhi((unsigned)task, p.inv_ndx) : task;  // = part * ns + strip
-      const int dx = task - row * ndx;        // window-relative horizontal offset, mvx = dx - R
-      const int part = I.ns == 1 ? row : (int)__umulhi((unsigned)row, I.inv_ns);  // (2^32 / 1 does not fit)
-      const int st = row - part * I.ns;
-      const int u = p.e + st * SW + dx;       // byte offset of the candidate column in a window row
-      const uint32_t shift = 8u * (uint32_t)(u & 3);
-      // vertical part: candidates [c0, c0 + L), evenly spread, the last one ends at nc
-      const int c0 = I.nparts > 1 ? (int)(((long long)(I.nc - L) * part) / (I.nparts - 1)) : 0;
-
-      // ---- current-frame rows of the strip into registers
-      uint32_t cur[BH][WORDS];
-      {
-        const uint4 *ct = reinterpret_cast<const uint4 *>(sb + cur_off);
-        const int pitch4 = p.cur_pitch >> 4;
-#pragma unroll
-        for (int r = 0; r < BH; r++)
-#pragma unroll
-          for (int q = 0; q < WORDS / 4; q++) {
-            const uint4 v = ct[r * pitch4 + st * (WORDS / 4) + q];
-            cur[r][4 * q + 0] = v.x; cur[r][4 * q + 1] = v.y; cur[r][4 * q + 2] = v.z; cur[r][4 * q + 3] = v.w;
-          }
-      }
-
-      uint32_t acc[NSUB][BH];
-      uint32_t bestk[NSUB];
-#pragma unroll
-      for (int b = 0; b < NSUB; b++) bestk[b] = kNoKey;
-
-      const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sb + (size_t)(I.dy_lo + c0) * kWinPitch) + (u >> 2);
-      constexpr int pitchw = kWinPitch >> 2;
-      const int x_strip = (I.strip0 + st) * SW;
-      // window-relative dy of the candidate that finishes at step s of period 0 is dy_fin + s
-      // (FORM 3: relative to the part's first candidate row dy_base, so that it fits 7 bits)
-      const int dy_base = I.dy_lo + c0;
-      int dy_fin = (FORM == 3 ? 0 : dy_base) - (BH - 1);
-
-      // FORM 1 state: sum cur^2 + sliding sum of the reference row energies, and their history
-      uint32_t srun[NSUB], qh[NSUB][BH], msk[WORDS];
-      const bool half = I.h != BH;          // bottom block row of height BH/2
-      constexpr bool kBiased = FORM == 2 && BH == 8;   // see kBias8
-      if (FORM >= 1 && FORM < 3 && !kBiased) {
-#pragma unroll
-        for (int b = 0; b < NSUB; b++) {
-          uint32_t a4[4] = {0u, 0u, 0u, 0u};  // four independent IDP chains instead of one long one
-#ifndef ME_EXPERIMENT_NOCURSQ   // (experiment only, wrong results: what would dropping sum cur^2 from the tasks be worth?)
-#pragma unroll
-          for (int r = 0; r < BH; r++)
-#pragma unroll
-            for (int w = 0; w < WPB; w++)
-              a4[(r * WPB + w) & 3] = __dp4a(cur[r][b * WPB + w], cur[r][b * WPB + w], a4[(r * WPB + w) & 3]);
-#endif
-          srun[b] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-#pragma unroll
-          for (int r = 0; r < BH; r++) qh[b][r] = 0u;
-        }
-        if (PW && FORM == 1) {
-#pragma unroll
-          for (int w = 0; w < WORDS; w++) {
-            // bytes of word w that lie inside the frame for the block at x_strip (columns < W)
-            const int left = p.W - (x_strip + 4 * w);
-            msk[w] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
-          }
-        }
-      }
-
-      // FORM 4 (SSIM cost) state.  The dot product sum r*c is the only per-pixel work (me_ssim.cu header); a finished
-      // candidate takes the division-free bound against thr4 (the best score this block has reached so far: the
-      // shared key at the start of the chunk, then this thread's own evaluations) and, if it survives, waits in the
-      // thread's queue for the full evaluation at the end of the period -- where the lanes evaluate TOGETHER
-      // instead of one divergent lane at a time in the middle of the unrolled loop.
-      float sc4 = 0.0f, thr4 = 0.0f;
-      int A4 = 0, imc4 = 0, sumc4 = 0, col4 = 0;
-      unsigned long long best4 = 0ull;
-      uint32_t *qbase = nullptr, *qptr = nullptr;
-      const int2 *spf8 = nullptr;
-      if constexpr (FORM == 4) {
-        const int bx = I.strip0 + st;
-        // horizontal clamp (main_ssim.c:22-25): candidate column x0 + dx - R must lie in [0, W - 16]
-        const bool ok = active && (x_strip + dx - p.R >= 0) && (x_strip + dx - p.R <= p.W - BW);
-        const int2 cs = __ldg(p.blk_stats + ((size_t)I.pair * p.by_count + (I.by - p.by_begin)) * p.nbx_full + bx);
-        sumc4 = cs.x;
-        sc4 = __int_as_float(cs.y);                      // ssim.c:53
-        imc4 = cs.x >> 8;                                // (int)mean of the current block, ssim.c:54 (ssim.h:12)
-        A4 = cs.x - 256 * imc4;                          // sum (c - imc)
-        // lanes outside the clamp (and idle lanes) never pass the bound: thr = +inf
-        thr4 = ok ? __uint_as_float((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&best[st]) >> 32))
-                  : __int_as_float(0x7f800000);
-        qbase = reinterpret_cast<uint32_t *>(smem + p.q_off) + threadIdx.x;
-        qptr = qbase;
-        // ... and they look up a column inside the clamp: table entries right of W - 16 are never written
-        const int dxv = min(max(dx, p.R - x_strip), p.W - BW - x_strip + p.R);
-        col4 = p.e_s + st * SW + dxv;
-        spf8 = reinterpret_cast<const int2 *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * p.s_pitch + col4;
-      }
-      // the queued candidates of every lane, evaluated together (ssim.c:54-58); key = score bits << 32 | ~visit index,
-      // so the maximum is the first strict maximum in y-major/x-minor order (ssim.c:98-106)
-      auto drain4 = [&]() {
-        const unsigned long long before = best4;
-        if (p.dbg && lane == 0) atomicAdd(p.dbg + 4, 1ull);
-        const bool any_pending = __any_sync(0xffffffffu, qptr != qbase);
-        if (p.dbg && lane == 0 && any_pending) atomicAdd(p.dbg + 0, 1ull);
-        while (__any_sync(0xffffffffu, qptr != qbase)) {
-          if (p.dbg && lane == 0) atomicAdd(p.dbg + 1, 1ull);
-          if (qptr != qbase) {
-            if (p.dbg) atomicAdd(p.dbg + 2, 1ull);
-            qptr -= kThreads;
-            const uint32_t k = *qptr;
-            const int dyr = (int)(k & 0xffu);
-            const int2 ent = reinterpret_cast<const int2 *>(sb + s_off)[dyr * p.s_pitch + col4];
-            const int sumr = ent.x;
-            const float sr = __int_as_float(ent.y);
-            const int is = (int)(k >> 8) - (sumr >> 8) * A4 - imc4 * sumr;     // sum (r - imr)(c - imc), exact
-            const float cross = __fmul_rn((float)is, 1.0f / 256.0f);          // ssim.c:39
-            const float num = __fadd_rn(cross, kC3());
-            const float den = __fadd_rn(__fmul_rn(sr, sc4), kC3());
-            if (__fmul_rn(num, kPruneMargin()) >= __fmul_rn(thr4, den)) {      // the threshold may have risen since
-              const float sc = ssim_from_stats(__fmul_rn((float)sumr, 1.0f / 256.0f), sr,
-                                               __fmul_rn((float)sumc4, 1.0f / 256.0f), sc4, cross);
-              if (p.dbg) atomicAdd(p.dbg + 3, 1ull);
-              if (sc > 0.0f) {
-                const uint32_t vis = ((uint32_t)dyr << 16) | (uint32_t)dx;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (0xffffffffu - vis);
-                best4 = key > best4 ? key : best4;
-                thr4 = fmaxf(thr4, sc);
-              }
-            }
-          }
-        }
-        // a better score is shared with the other warps of the block right away (they pick it up at their next
-        // period), not only at the end of the chunk
-        if (best4 != before) atomicMax(&best[st], best4);
-      };
-
-      // Software pipeline: the raw words of the NEXT row are loaded at the top of a step, so
-      // the LDS latency and the funnel shifts hide behind a whole step of IDP work (the row
-      // after the last one still lies inside the stage; it is loaded but never used).
-      uint32_t raw[WORDS + 1];
-#pragma unroll
-      for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
-      rowp += pitchw;
-
-      // the period count is the same for the whole warp; routing it through a warp reduction puts
-      // it in a uniform register, so the ramp branches below compile to uniform branches without
-      // divergence bookkeeping (BSSY/BSYNC)
-      const int m_uni = __reduce_max_sync(0xffffffffu, I.m);
-      // FORM 2: energy-table entry of the candidate that finishes at step 0 of the current period
-      // (only dereferenced for candidates that exist)
-      const int s_pitch = p.s_pitch;
-      const uint32_t *spf = reinterpret_cast<const uint32_t *>(sb + s_off) + (I.dy_lo + c0 - (BH - 1)) * s_pitch +
-                            p.e_s + st * SW + dx;
-      // one period of BH steps.  first_c / last_c are plain bools (one code copy whose ramp branches are warp-uniform
-      // run-time branches: BoolRt) or compile-time tags (BoolTag: a copy per period kind without those branches)
-      auto period_body = [&](const auto first_c, const auto last_c) {
-        const bool first = first_c.value;
-        const bool last = last_c.value;
-        if constexpr (FORM == 4)   // the block's best score so far, whoever found it (+inf stays +inf)
-          thr4 = fmaxf(thr4, __uint_as_float((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&best[st]) >> 32)));
-#pragma unroll
-        for (int s_ = 0; s_ < BH; s_++) {
-          // byte-align this row to the candidate column, then fetch the next row
-          uint32_t ref[WORDS];
-#ifdef ME_EXPERIMENT_NOLOAD
-#pragma unroll
-          for (int w = 0; w < WORDS; w++) ref[w] = raw[w] + (uint32_t)s_;
-#else
-#pragma unroll
-          for (int w = 0; w < WORDS; w++) ref[w] = __funnelshift_r(raw[w], raw[w + 1], shift);
-#pragma unroll
-          for (int w = 0; w <= WORDS; w++) raw[w] = rowp[w];
-          rowp += pitchw;
-#endif
-
-#ifndef ME_EXPERIMENT_NOQ
-          if (FORM == 1) {
-            // energy of this reference row over each block's columns (bytes right of the frame
-            // masked out when PW), as two independent IDP chains, then slide the window:
-            // full height: + q(t) - q(t-BH);  half height: + q(t-BH/2) - q(t-BH)
-#pragma unroll
-            for (int b = 0; b < NSUB; b++) {
-              uint32_t q0 = 0, q1 = 0;
-#pragma unroll
-              for (int w = 0; w < WPB; w++) {
-                const uint32_t x = ref[b * WPB + w];
-                const uint32_t xm = PW ? (x & msk[b * WPB + w]) : x;
-                if (w & 1) q1 = __dp4a(xm, x, q1);
-                else q0 = __dp4a(xm, x, q0);
-              }
-              const uint32_t qt = q0 + q1;
-              const uint32_t add = half ? qh[b][(s_ + BH / 2) % BH] : qt;
-              srun[b] = srun[b] + add - qh[b][s_];
-              qh[b][s_] = qt;
-            }
-          }
-#endif
-
-          // one (current row r) x (this reference row) group: slot (s_ - r) mod BH
-          auto group = [&](const int r) {
-            const int slot = (s_ - r + BH) % BH;
-#pragma unroll
-            for (int b = 0; b < NSUB; b++) {
-              uint32_t a = (r == 0) ? 0u : acc[b][slot];
-#pragma unroll
-              for (int w = 0; w < WPB; w++) {
-                if (FORM >= 1) {
-                  a = __dp4a(cur[r][b * WPB + w], ref[b * WPB + w], a);
-                } else {
-                  const uint32_t d = __vabsdiffu4(cur[r][b * WPB + w], ref[b * WPB + w]);
-                  a = __dp4a(d, d, a);
-                }
-              }
-              acc[b][slot] = a;
-              if (r == BH - 1 && FORM == 4) {
-                // candidate complete (SSIM cost): cross term and the division-free bound; survivors are queued.
-                // (>= instead of !(<): identical for the finite values of real candidates)
-                const int2 ent = *spf8;
-                const int sumr = ent.x;
-                const int is = (int)a - (sumr >> 8) * A4 - imc4 * sumr;
-                const float cross = __fmul_rn((float)is, 1.0f / 256.0f);
-                const float num = __fadd_rn(cross, kC3());
-                const float den = __fadd_rn(__fmul_rn(__int_as_float(ent.y), sc4), kC3());
-                if (__fmul_rn(num, kPruneMargin()) >= __fmul_rn(thr4, den)) {
-                  *qptr = (a << 8) | (uint32_t)(dy_fin + s_);
-                  qptr += kThreads;
-                }
-              } else if (r == BH - 1) {
-                // candidate complete: fold (ssd << 8 | dy) into the running minimum
-                uint32_t ssd = a;
-                if (FORM == 1) ssd = srun[b] - 2u * a;
-                if (FORM == 2 || FORM == 3) {
-                  // (A + E) - a - a: one IADD3 on the ALU pipe instead of an IMAD on the saturated FMA pipe
-                  // (8x8 and FORM 3: the table entry already holds E + bias and A is added back at publish time)
-                  const uint32_t ae = (kBiased || FORM == 3) ? spf[b * BW] : srun[b] + spf[b * BW];
-                  asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %2; }" : "=r"(ssd) : "r"(ae), "r"(a));
-                }
-                uint32_t key;
-                if constexpr (FORM == 3) {
-                  key = (ssd << 7) + (uint32_t)(dy_fin + s_);   // t << 7 | part-relative dy
-                } else if constexpr (BH == 8) {
-                  // ssd < 2^24 and dy < 2^8: a byte permute builds ssd << 8 | dy on the ALU pipe.  Left
-                  // to itself ptxas emits IMAD(ssd, 0x100, dy) here -- on the FMA-heavy pipe the
-                  // IDP.4A stream already saturates, where 8x8 blocks finish a candidate every 16 IDP
-                  key = __byte_perm(ssd, (uint32_t)(dy_fin + s_), 0x2104);
-                } else {
-                  key = (ssd << 8) + (uint32_t)(dy_fin + s_);
-                }
-                bestk[b] = min(bestk[b], key);
-              }
-            }
-          };
-#ifdef ME_EXPERIMENT_NOSKIP
-          // experiment only (wrong results): no ramp skipping, hence no branches in the step
-#pragma unroll
-          for (int r = 0; r < BH; r++) group(r);
-#else
-          // ramp-down (last period): candidates that started in this period do not exist -> only
-          // r >= s_; ramp-up (first period): candidates from the previous period do not exist ->
-          // only r <= s_.  The diagonal group r == s_ always runs; placed last it shares a basic
-          // block with the next step's shifts, loads and row energy, i.e. independent work.
-          if (!last) {
-#pragma unroll
-            for (int r = 0; r < s_; r++) group(r);
-          }
-          if (!first) {
-#pragma unroll
-            for (int r = s_ + 1; r < BH; r++) group(r);
-          }
-          group(s_);
-#endif
-          if (FORM == 2 || FORM == 3) spf += s_pitch;  // next step finishes the candidate one row further down
-          if (FORM == 4) spf8 += s_pitch;
-        }
-        dy_fin += BH;
-        if constexpr (FORM == 4) drain4();
-      };
-#ifndef ME_SPLIT_PERIODS
-#define ME_SPLIT_PERIODS 1
-#endif
-      if constexpr (ME_SPLIT_PERIODS && BH == 8 && (FORM == 1 || FORM == 2) && !PEER) {
-        // 8x8 blocks: a step holds only 32 IDP.4A, so the two ramp branches per step show (ncu: 0.5 stall cycles per
-        // issued instruction in branch_resolving, profiles/ncu_tiled_8x8_pm12_r02_*).  The three period kinds get
-        // their own unrolled copy (7.5 KB each or less: the instruction cache holds them).  Measured: 4K 8x8 +-12
-        // 49.4 -> 54.9 %, +-32 67.5 -> 74.6 %, Foreman CIF 40.3 -> 43.4 % of the peak.  16x16 keeps its single 25 KB
-        // copy: with two or four copies FORM 3 ran 3.6x SLOWER (22.7 % instead of 81.2 %; not investigated
-        // further -- instruction-cache capacity or spills in the bigger function).
-        if (m_uni == 0) {
-          period_body(BoolTag<true>{}, BoolTag<true>{});
-        } else {
-          period_body(BoolTag<true>{}, BoolTag<false>{});
-          for (int per = 1; per < m_uni; per++) period_body(BoolTag<false>{}, BoolTag<false>{});
-          period_body(BoolTag<false>{}, BoolTag<true>{});
-        }
-      } else {
-        for (int per = 0; per <= m_uni; per++) period_body(BoolRt{per == 0}, BoolRt{per == m_uni});
-      }
-
-      // ---- combine the lanes of each block, one 64-bit shared atomicMin per block
-      // (FORM 3: the keys of one group must share dy_base, i.e. the vertical part as well as the strip)
-      const unsigned peers = __match_any_sync(0xffffffffu, active ? (FORM == 3 ? row : st) : -1 - lane);
-      const bool leader = (peers & (0u - peers)) == (1u << lane);
-      if constexpr (FORM == 4) {
-        // 64-bit maximum over the lanes of the block (best4 is 0 for lanes outside the clamp: they never queue)
-        const uint32_t hi = (uint32_t)(best4 >> 32), lo = (uint32_t)best4;
-        const uint32_t mhi = __reduce_max_sync(peers, hi);
-        const uint32_t mlo = __reduce_max_sync(peers, hi == mhi ? lo : 0u);
-        if (leader && mhi != 0u) atomicMax(&best[st], ((unsigned long long)mhi << 32) | mlo);
-      }
-#pragma unroll
-      for (int b = 0; b < (FORM == 4 ? 0 : NSUB); b++) {
-        const int x0 = x_strip + b * BW;
-        // horizontal clamp (main.c:73,75): candidate column x0 + dx - R must lie in [0, W - w]
-        const int bw = min(BW, p.W - x0);
-        const bool ok = active && x0 < p.W && (x0 + dx - p.R >= 0) && (x0 + dx - p.R <= p.W - bw);
-        const uint32_t key = ok ? bestk[b] : kNoKey;
-        const uint32_t mkey = __reduce_min_sync(peers, key);
-        const uint32_t mdx = __reduce_min_sync(peers, key == mkey ? (uint32_t)dx : 0xffffu);
-        if (leader && mkey != kNoKey) {
-          if constexpr (FORM == 3)   // t << 24 | absolute dy << 16 | dx  (t has 25 bits, dy 8, dx 8)
-            atomicMin(&best[st * NSUB + b], ((unsigned long long)(mkey >> 7) << 24) |
-                                                ((unsigned long long)((mkey & 127u) + (uint32_t)dy_base) << 16) | mdx);
-          else
-            atomicMin(&best[st * NSUB + b], ((unsigned long long)mkey << 32) | mdx);
-        }
-      }
-    }
+#include "me_tiled_chunk.inc"
     // ---- leave the item; the last warp out publishes it and re-arms the stage
     __syncwarp();
     int prev = 0;
@@ -679,76 +480,13 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
     prev = __shfl_sync(0xffffffffu, prev, 0);
     if (prev == kWarps - 1) {
       __threadfence_block();
-      for (int b = lane; b < I.ns * NSUB; b += 32) {
-        const int bx = I.strip0 * NSUB + b;
-        if (bx < p.nbx) {
-          const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(&best[b]);
-          if constexpr (FORM == 4) {
-            // no candidate above 0: the reference never writes the vector (ssim.c:88-103) -- reported as MV (0,0),
-            // score 0, found = 0, as the other SSIM kernels do
-            const size_t oi4 = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
-            const uint32_t vis = 0xffffffffu - (uint32_t)key;
-            if (p.out.mvx) p.out.mvx[oi4] = key ? (int)(vis & 0xffffu) - p.R : 0;     // ssim.c:103
-            if (p.out.mvy) p.out.mvy[oi4] = key ? (int)(vis >> 16) - p.R : 0;         // ssim.c:104
-            if (p.out.ssd) p.out.ssd[oi4] = key ? 1u : 0u;
-            if (p.out.score) p.out.score[oi4] = __uint_as_float((uint32_t)(key >> 32));
-            continue;
-          }
-          // key layouts: ssd << 40 | dy << 32 | dx;  FORM 3: t << 24 | dy << 16 | dx (t << 8 | dy would need 33 bits)
-          const uint32_t k32 = FORM == 3 ? (uint32_t)(key >> 16) : (uint32_t)(key >> 32);   // low byte: dy
-          const uint32_t kdx = FORM == 3 ? (uint32_t)key & 0xffffu : (uint32_t)key;
-          uint32_t ssd = FORM == 3 ? (uint32_t)(key >> 24) : k32 >> 8;
-          if constexpr (FORM == 3) {
-            // un-bias: ssd = t - kBias16 + sum cur^2 of this block, from the stage's current tile (the rows
-            // below a half-height block are zero-filled by the TMA load)
-            const uint32_t *ct = reinterpret_cast<const uint32_t *>(sb + cur_off) + b * (BW / 4);
-            uint32_t a2[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int r = 0; r < BH; r++)
-#pragma unroll
-              for (int w = 0; w < BW / 4; w++) {
-                const uint32_t v = ct[r * (p.cur_pitch >> 2) + w];
-                a2[w & 3] = __dp4a(v, v, a2[w & 3]);
-              }
-            ssd = ssd - kBias16 + ((a2[0] + a2[1]) + (a2[2] + a2[3]));
-          }
-          if constexpr (FORM == 2 && BH == 8) {
-            // un-bias: ssd = t - kBias8 + sum cur^2 of this block, from the stage's current tile (rows
-            // below a half-height block are zero-filled by the TMA load)
-            const uint32_t *ct = reinterpret_cast<const uint32_t *>(sb + cur_off) + b * (BW / 4);
-            uint32_t a2 = 0;
-#pragma unroll
-            for (int r = 0; r < BH; r++)
-#pragma unroll
-              for (int w = 0; w < BW / 4; w++) {
-                const uint32_t v = ct[r * (p.cur_pitch >> 2) + w];
-                a2 = __dp4a(v, v, a2);
-              }
-            ssd = ssd - kBias8 + a2;
-          }
-          const size_t oi = (size_t)I.pair * p.nbx * p.nby + (size_t)I.by * p.nbx + bx;
-          if (p.out.mvx) p.out.mvx[oi] = (int)kdx - p.R;             // main.c:58
-          if (p.out.mvy) p.out.mvy[oi] = (int)(k32 & 0xff) - p.R;    // main.c:59
-          if (p.out.ssd) p.out.ssd[oi] = ssd;
-          const int bw = min(BW, p.W - bx * BW);
-          if (p.out.score) p.out.score[oi] = __fdiv_rn((float)ssd, (float)(bw * I.h));  // main.c:27
-          if constexpr (PEER) {
-            const float score = __fdiv_rn((float)ssd, (float)(bw * I.h));
-            // same four values into every peer's copy of the field (a separate instantiation: the
-            // plain kernel's code is untouched -- its placement is worth more than 1 %)
-            for (int q = 0; q < p.npeer; q++) {
-              const Out &po = p.peer[q];
-              if (po.mvx) po.mvx[oi] = (int)kdx - p.R;
-              if (po.mvy) po.mvy[oi] = (int)(k32 & 0xff) - p.R;
-              if (po.ssd) po.ssd[oi] = ssd;
-              if (po.score) po.score[oi] = score;
-            }
-          }
-        }
-      }
+      if (lane == 0) ME_TRACE(it, 5, trace_set);
+#include "me_tiled_publish.inc"
       __syncwarp();
-      refill(stage);
+      if (lane == 0) ME_TRACE(it, 6, trace_set);
+      refill(stage, 0u);
     }
+  }
   }
 }
 
@@ -1462,6 +1200,12 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
     }
     p.next_item = d_ctr;
   }
+#ifdef ME_TRACE_ITEMS
+  if (FORM != 4 && getenv("ME_B200_TRACE_ITEMS")) {
+    if (cudaMalloc((void **)&p.dbg, (size_t)p.total_items * 64) == cudaSuccess) cudaMemset(p.dbg, 0, (size_t)p.total_items * 64);
+    else p.dbg = nullptr;
+  }
+#endif
   p.q_off = p.stages * p.stage_bytes;
   const int smem = p.stages * p.stage_bytes + queue_bytes;
   if (getenv("ME_B200_VERBOSE"))
@@ -1498,6 +1242,39 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
   }
   plan->kernels_launched++;
   e = cudaGetLastError();
+#ifdef ME_TRACE_ITEMS
+  if (FORM != 4 && p.dbg) {
+    cudaStreamSynchronize(s);
+    const size_t n = (size_t)p.total_items;
+    unsigned long long *h = (unsigned long long *)malloc(n * 64);
+    cudaMemcpy(h, p.dbg, n * 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    double d[6] = {0, 0, 0, 0, 0, 0};
+    size_t cnt = 0;
+    unsigned long long sm_first[256], sm_last[256];
+    for (int i = 0; i < 256; i++) { sm_first[i] = ~0ull; sm_last[i] = 0; }
+    for (size_t i = 0; i < n; i++) {
+      const unsigned long long *t = h + i * 8;
+      if (!t[6] || t[3] == ~0ull) continue;
+      d[0] += (double)(t[1] - t[0]); d[1] += (double)(t[2] - t[1]); d[2] += (double)((long long)(t[3] - t[2]));
+      d[3] += (double)((long long)(t[4] - t[3])); d[4] += (double)((long long)(t[5] - t[4])); d[5] += (double)(t[6] - t[5]);
+      const int sm = (int)(t[7] & 255);
+      if (t[0] < sm_first[sm]) sm_first[sm] = t[0];
+      if (t[6] > sm_last[sm]) sm_last[sm] = t[6];
+      cnt++;
+    }
+    double span = 0; int nsm = 0;
+    for (int i = 0; i < 256; i++) if (sm_last[i]) { span += (double)(sm_last[i] - sm_first[i]); nsm++; }
+    if (cnt)
+      fprintf(stderr, "[me_b200 item trace] %zu items on %d SMs, SM span %.0f clk; per item (clk): global atomic %.0f, decode+TMA issue %.0f, "
+              "TMA issued -> first warp has the data %.0f, first warp -> last chunk handed out %.0f, last chunk -> last warp leaves %.0f, "
+              "publish %.0f; items per SM %.1f => stage cycle budget %.0f clk per item per SM\n",
+              cnt, nsm, span / nsm, d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[4] / cnt, d[5] / cnt, (double)cnt / nsm,
+              span / nsm / ((double)cnt / nsm));
+    free(h);
+    p.dbg = nullptr;
+  }
+#endif
   if (FORM == 4 && p.dbg) {   // measurements only
     unsigned long long h[8] = {0};
     cudaStreamSynchronize(s);
