@@ -16,4 +16,16 @@ for form in ("2", "1"):
             out = est.search_u8(np.stack([cur, ref]), np.stack([ref, ref]))
             assert est.kernel_in_use == me.ME_KERNEL_TILED
             assert not out["ssd"][1].any()
+# the SSIM cost, on its own streaming kernel and as the tiled kernel's FORM 4
+os.environ.pop("ME_B200_FORM", None)
+for f4 in ("0", "1"):
+    os.environ["ME_B200_SSIM_FORM4"] = f4
+    with me.Estimator(352, 288, 16, 12, max_pairs=2, cost=me.ME_COST_SSIM) as est:
+        out = est.search_u8(np.stack([cur, ref]), np.stack([ref, ref]))
+        assert (out["mvx"][1] == 0).all() and (out["mvy"][1] == 0).all()
+os.environ.pop("ME_B200_SSIM_FORM4", None)
+# small spans: the TMA-fed streaming kernel
+with me.Estimator(352, 288, 16, 2, max_pairs=2) as est:
+    out = est.search_u8(np.stack([cur, ref]), np.stack([ref, ref]))
+    assert not out["ssd"][1].any()
 print("sanitize_case ok")
