@@ -92,6 +92,32 @@ def workload_config(name, pairs, world):
             "cost": ["mse", "ssim"][cost], "search": ["full", "three_step", "diamond"][search]}
 
 
+def plan_ingest_helpers(bw, nd, slot_pairs, hp_force=0):
+    """Which ranks send part of every submit over a peer GPU's host link (me_b200_set_ingest_helper), and how much.
+    bw[r] = copy-only H2D rate of rank r with ALL ranks copying (GB/s), nd[r] = what its kernel consumes.
+    Deterministic greedy pairing, the same on every rank: most starved rank first, donor with most spare.  The detour is
+    sized to the deficit (rounded, not rounded up) and never takes more than 80 % of the donor's spare link rate: a donor
+    driven to 100 % of its own link becomes the slowest rank itself (measured: 4 of 16 pairs over donors with 7.4 GB/s
+    spare made the 8-GPU end-to-end rate 4 % worse than no helper at all).  Returns {rank: (helper GPU, pairs per submit)}.
+    hp_force > 0 (experiments) fixes the pairs per submit."""
+    world = len(bw)
+    frac = {r: 1.0 - 0.96 * bw[r] / nd[r] for r in range(world)}      # share of the bytes that must detour
+    spare = {r: bw[r] - nd[r] for r in range(world)}
+    helpers = {}
+    for r in sorted((r for r in range(world) if frac[r] > 0.0), key=lambda r: -frac[r]):
+        donors = [d for d in range(world) if d != r and frac[d] <= 0.0 and d not in (h[0] for h in helpers.values())]
+        if not donors:
+            continue
+        d = max(donors, key=lambda d: spare[d])
+        hp = max(1, int(round(slot_pairs * frac[r])))
+        hp = min(hp, int(0.8 * spare[d] / nd[r] * slot_pairs), slot_pairs - 1)
+        if hp_force > 0:
+            hp = min(hp_force, slot_pairs - 1)
+        if hp >= 1:
+            helpers[r] = (d, hp)
+    return helpers
+
+
 def make_batch(name, pairs, rank):
     """Deterministic synthetic batch (pairs, H, W) uint8 x2; a different seed per pair and rank."""
     import motionestimation_b200 as me
@@ -564,25 +590,7 @@ def main():
         bw = [float(v[0].item()) for v in allv]
         nd = [float(v[1].item()) for v in allv]
         del pd
-        # deterministic greedy pairing, the same on every rank: most starved rank first, donor with most spare.
-        # The detour is sized to the deficit (rounded, not rounded up) and never takes more than 80 % of the
-        # donor's spare link rate: a donor driven to 100 % of its own link becomes the slowest rank itself
-        # (measured: 4 of 16 pairs over donors with 7.4 GB/s spare made the 8-GPU end-to-end rate 4 % worse).
-        frac = {r: 1.0 - 0.96 * bw[r] / nd[r] for r in range(world)}      # share of the bytes that must detour
-        spare = {r: bw[r] - nd[r] for r in range(world)}
-        hp_force = int(os.environ.get("BENCH_INGEST_HP", "0"))            # experiments: pairs per submit to detour
-        helpers = {}
-        for r in sorted((r for r in range(world) if frac[r] > 0.0), key=lambda r: -frac[r]):
-            donors = [d for d in range(world) if d != r and frac[d] <= 0.0 and d not in (h[0] for h in helpers.values())]
-            if not donors:
-                continue
-            d = max(donors, key=lambda d: spare[d])
-            hp = max(1, int(round(slot_pairs * frac[r])))
-            hp = min(hp, int(0.8 * spare[d] / nd[r] * slot_pairs), slot_pairs - 1)
-            if hp_force > 0:
-                hp = min(hp_force, slot_pairs - 1)
-            if hp >= 1:
-                helpers[r] = (d, hp)
+        helpers = plan_ingest_helpers(bw, nd, slot_pairs, int(os.environ.get("BENCH_INGEST_HP", "0")))
         helper_error = None
         if rank in helpers:
             try:   # (local rank == device index on one node; needs every GPU visible to every rank + peer access)

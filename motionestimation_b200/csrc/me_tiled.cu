@@ -1047,6 +1047,7 @@ cudaError_t launch_shape_pw(TiledPlan *plan, const Geom &g, const Frames &f, int
       const int L = m * BH + 1;
       const int nparts = (nc + L - 1) / L;
       const long long chunks = ((long long)ns * nc * nparts + 31) / 32;
+      if (chunks > 2000) continue;   // the stage queue's hand-out word holds 11 bits of chunk count (+ 16 of overshoot)
       // per task: L candidates x BH rows x WORDS cross-term ops (x2 for FORM 0), plus per streamed
       // row the loads, shifts and (FORM 1) the row-energy ops
       const double per_row = FORM == 1 ? (2.0 * WORDS + 8.0) : (2.0 * WORDS + 6.0);

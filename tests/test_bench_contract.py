@@ -86,3 +86,20 @@ def test_both_arms_build_the_same_config():
     d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "foreman_8x8_pm12", "--gpus", "1")
     assert d["config"] == bench.workload_config("foreman_8x8_pm12", 512, 1)
     assert d["config"]["l2"] and d["config"]["parallelism"] == "frame-pair sharding x1"
+
+
+def test_ingest_helper_plan_is_conservative():
+    """bench.plan_ingest_helpers: starved ranks borrow at most 80 % of a donor's spare host-link rate; the numbers are
+    the ones measured on the pool's 8-GPU box (profiles/h2d_probe_r02.txt; GPUs 0-3 share one uplink)."""
+    import bench
+    bw = [24.3, 24.2, 24.3, 24.3, 37.6, 37.9, 38.1, 38.0]
+    plan = bench.plan_ingest_helpers(bw, [29.5] * 8, 16)
+    assert sorted(plan) == [0, 1, 2, 3]                          # the four GPUs behind the shared uplink
+    assert sorted(h[0] for h in plan.values()) == [4, 5, 6, 7]   # one donor each
+    assert all(h[1] == 3 for h in plan.values())                 # 3 of 16 pairs: 5.5 GB/s of 8.3 GB/s spare
+    # a kernel that needs less than every link delivers: nobody detours
+    assert bench.plan_ingest_helpers(bw, [20.0] * 8, 16) == {}
+    # donors without spare capacity are not used
+    assert bench.plan_ingest_helpers([24.0, 24.0, 30.0, 30.0], [29.5] * 4, 16) == {}
+    # the same plan on every rank (pure function of the gathered numbers), and the forced variant for experiments
+    assert bench.plan_ingest_helpers(bw, [29.5] * 8, 16, hp_force=2)[0][1] == 2
