@@ -253,6 +253,10 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #define ME_QUEUE_ALL 0
 #endif
   constexpr bool kQueue = BH == 8 || ME_QUEUE_ALL;
+#ifndef ME_BALLOT_DX
+#define ME_BALLOT_DX 1
+#endif
+  constexpr bool kBallotDx = ME_BALLOT_DX && BH == 8 && FORM != 4;   // chunk epilogue, me_tiled_chunk.inc
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
   // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
