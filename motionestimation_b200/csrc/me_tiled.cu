@@ -256,7 +256,10 @@ tiled_search_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_co
 #ifndef ME_BALLOT_DX
 #define ME_BALLOT_DX 1
 #endif
-  constexpr bool kBallotDx = ME_BALLOT_DX && BH == 8 && FORM != 4;   // chunk epilogue, me_tiled_chunk.inc
+  // chunk epilogue (me_tiled_chunk.inc): warp vote instead of a second masked reduction for the dx of the winner.
+  // 8x8 kernels only: for FORM 3 (-DME_BALLOT_DX=2) it measured +1.5 % at +-8 / +-64 but -1.1 % on the headline
+  // geometry (code placement), so 16x16 keeps the two reductions.
+  constexpr bool kBallotDx = (ME_BALLOT_DX && BH == 8 && FORM != 4) || (ME_BALLOT_DX == 2 && FORM == 3);
   const int nblk_item = p.ns * NSUB;  // key slots per stage
 
   // (re)arm a stage: take the next item from the launch-wide counter (items are handed out in
